@@ -1,0 +1,180 @@
+/* ullsam.h — C ABI of libullsam_b200.so: the B200-native (sm_100a) SAM segmentation branch of uLLSAM.
+ *
+ * This is the drop-in boundary for the one hot path this repository accelerates:
+ *   ImageEncoderViT.forward   (reference modeling/image_encoder.py:106-116)
+ *   MaskDecoder.forward       (reference modeling/mask_decoder.py:71-149)
+ *   TwoWayTransformer.forward (reference modeling/transformer.py:62-108)
+ * The reference has no FFI layer of its own (it is pure Python/PyTorch); the Python shims in
+ * ullsam_b200/modeling/ keep the reference's nn.Module API and bind these entry points with ctypes
+ * (see INTEGRATION.md for the stub a maintainer would add to the reference).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.  Every function returns 0 or a negative
+ *     ullsam_status; nothing throws across the ABI.  ullsam_last_error() gives the text.
+ *   - unless a name ends in _host, every data pointer is a DEVICE pointer owned by the caller, the
+ *     call is asynchronous on `stream` (a cudaStream_t passed as void*), and nothing synchronises.
+ *   - one handle per (device, model).  A handle is not thread-safe; distinct handles are independent.
+ *   - there is no CPU fallback anywhere: without an sm_100 device every compute call fails.
+ */
+#ifndef ULLSAM_H_
+#define ULLSAM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ULLSAM_ABI_VERSION 1
+
+typedef enum {
+  ULLSAM_OK = 0,
+  ULLSAM_ERR_INVALID = -1,    /* bad argument / shape / unknown key */
+  ULLSAM_ERR_CUDA = -2,       /* a CUDA runtime or driver call failed */
+  ULLSAM_ERR_NO_DEVICE = -3,  /* no sm_100 device (there is no fallback path) */
+  ULLSAM_ERR_STATE = -4,      /* weights missing / handle not ready */
+  ULLSAM_ERR_NOMEM = -5
+} ullsam_status;
+
+typedef enum { ULLSAM_F32 = 0, ULLSAM_BF16 = 1, ULLSAM_F16 = 2 } ullsam_dtype;
+
+/* Hyper-parameters: the arguments of ImageEncoderViT.__init__ (image_encoder.py:18-36),
+ * TwoWayTransformer.__init__ (transformer.py:17-25) and MaskDecoder.__init__ (mask_decoder.py:17-26)
+ * as fixed by build_sam._build_sam (build_sam.py:55-98). */
+typedef struct {
+  int32_t img_size;      /* 1024 */
+  int32_t patch_size;    /* 16   */
+  int32_t in_chans;      /* 3    */
+  int32_t embed_dim;     /* 768 (vit_b) / 1024 (vit_l) / 1280 (vit_h); multiple of 64 */
+  int32_t depth;         /* 12 / 24 / 32 */
+  int32_t num_heads;     /* embed_dim / 64 */
+  int32_t mlp_dim;       /* embed_dim * mlp_ratio */
+  int32_t out_chans;     /* 256 */
+  int32_t window_size;   /* 14 */
+  int32_t num_global;    /* number of valid entries in global_attn_indexes */
+  int32_t global_attn_indexes[8];
+  float enc_ln_eps;      /* 1e-6 (build_sam.py:72) */
+  /* decoder */
+  int32_t transformer_dim; /* 256 */
+  int32_t dec_depth;       /* 2 */
+  int32_t dec_heads;       /* 8 */
+  int32_t dec_mlp_dim;     /* 2048 */
+  int32_t num_mask_tokens; /* num_multimask_outputs + 1 = 4 */
+  int32_t iou_head_hidden; /* 256 */
+  int32_t iou_head_depth;  /* 3 */
+} ullsam_config;
+
+typedef struct ullsam_handle ullsam_handle;
+
+int ullsam_abi_version(void);
+
+/* Text of the most recent failure on this handle (or, with h == NULL, of the last failed
+ * ullsam_create on this thread).  Never NULL. */
+const char* ullsam_last_error(const ullsam_handle* h);
+
+/* Replaces the construction of the three modules in build_sam._build_sam (build_sam.py:66-98). */
+int ullsam_create(const ullsam_config* cfg, int device, ullsam_handle** out);
+void ullsam_destroy(ullsam_handle* h);
+
+/* Replaces nn.Module.load_state_dict for the path (build_sam.py:103-106; key names SURVEY App. B,
+ * e.g. "image_encoder.blocks.3.attn.qkv.weight", "mask_decoder.iou_token.weight").
+ * `data` may be a host or device pointer; it is copied and re-packed into the kernels' layouts
+ * (bf16 GEMM operands, fp32 vectors) before the call returns — the caller keeps ownership. */
+int ullsam_set_weight(ullsam_handle* h, const char* state_dict_key, const void* data, int dtype,
+                      const int64_t* shape, int ndim);
+/* Number of state_dict tensors still missing (0 when both modules are fully loaded). */
+int ullsam_missing_weights(const ullsam_handle* h, int which /*0 encoder, 1 decoder*/);
+
+/* Workspace the handle will hold for an encoder batch of B images / a decoder batch of R
+ * (image, prompt) pairs.  Allocated lazily with cudaMalloc and kept until destroy. */
+size_t ullsam_workspace_bytes(const ullsam_handle* h, int B, int R);
+
+/* ImageEncoderViT.forward (image_encoder.py:106-116).
+ * images : [B, 3, 1024, 1024] NCHW, dtype in {F32, BF16}
+ * out_emb: [B, 256, 64, 64]   NCHW, out_dtype in {F32, BF16} */
+int ullsam_encoder_forward(ullsam_handle* h, const void* images, int dtype, int B, void* out_emb,
+                           int out_dtype, void* stream);
+
+/* MaskDecoder.forward (mask_decoder.py:71-109) for n_img images x P prompts each; pair r = i*P + j
+ * uses image i (the reference's repeat_interleave at mask_decoder.py:126; n_img == 1 is the
+ * reference's own calling convention, n_img > 1 with P == 1 is the concatenation of per-image calls
+ * made by Sam.forward, sam.py:101-117).
+ * emb      : [n_img, 256, 64, 64] fp32 NCHW          image_pe: [256, 64, 64] fp32
+ * sparse   : [n_img*P, Ns, 256] fp32
+ * dense    : dense_mode 0: [dense_batch, 256, 64, 64] fp32, dense_batch in {1, n_img*P}
+ *            dense_mode 1: [dense_batch, 256] fp32 — one vector per pair broadcast over the 64x64
+ *                          grid (PromptEncoder's no_mask_embed expand, prompt_encoder.py:196-199)
+ * masks    : [n_img*P, multimask ? 3 : 1, 256, 256] fp32      iou: [n_img*P, multimask ? 3 : 1] fp32 */
+int ullsam_decoder_forward(ullsam_handle* h, const void* emb, int n_img, const void* image_pe,
+                           const void* sparse, int P, int Ns, const void* dense, int dense_mode,
+                           int dense_batch, int multimask, void* masks, void* iou, void* stream);
+
+/* Same contract as MaskDecoder.predict_masks (mask_decoder.py:112-149): all 4 masks / IoUs. */
+int ullsam_decoder_predict_masks(ullsam_handle* h, const void* emb, int n_img, const void* image_pe,
+                                 const void* sparse, int P, int Ns, const void* dense, int dense_mode,
+                                 int dense_batch, void* masks4, void* iou4, void* stream);
+
+/* TwoWayTransformer.forward (transformer.py:62-108).
+ * image_embedding, image_pe: [R, 256, 64, 64] / [256, 64, 64] fp32; point_embedding: [R, Nt, 256] fp32
+ * queries: [R, Nt, 256] fp32; keys: [R, 4096, 256] fp32 */
+int ullsam_transformer_forward(ullsam_handle* h, const void* image_embedding, int R, const void* image_pe,
+                               const void* point_embedding, int Nt, void* queries, void* keys, void* stream);
+
+/* End-to-end with HOST buffers (pinned or pageable): H2D of the images and prompts, encoder,
+ * decoder (one prompt set per image), D2H of masks / iou / optionally embeddings; synchronises
+ * before returning.  This is the call bench.py times for the `e2e` figure. */
+int ullsam_segment_host(ullsam_handle* h, const float* images_host, int B, const float* image_pe_host,
+                        const float* sparse_host, int Ns, const float* dense_vec_host, int multimask,
+                        float* masks_host, float* iou_host, float* emb_host /* may be NULL */);
+
+/* ---- operator-level entry points (the unit the parity tests exercise) ------------------------ */
+
+/* tcgen05 GEMM: C = A[M,K] x W[N,K]^T with a fused epilogue.  Mirrors ullsam::GemmParams. */
+typedef struct {
+  int32_t epi;  /* 0 bf16 | 1 +residual fp32 | 2 qkv split | 3 +pos fp32 | 4 LN2d bf16 | 5 LN2d NCHW | 6 fp32 */
+  int32_t M, N, K;
+  int32_t a_conv3, conv_c;
+  const void* A;     /* bf16 */
+  const void* W;     /* bf16 [N,K] */
+  const float* bias; /* may be NULL */
+  void* out;
+  int32_t ldc;
+  int32_t act;       /* 0 none | 1 GELU(erf) | 2 ReLU */
+  const float* residual;
+  const float* pos;
+  int32_t pos_rows;
+  void* q;
+  void* k;
+  void* v;
+  int32_t T, heads;
+  const float* ln_w;
+  const float* ln_b;
+  float ln_eps;
+  int32_t hw;
+} ullsam_gemm_desc;
+int ullsam_op_gemm(const ullsam_gemm_desc* d, void* stream);
+
+/* nn.LayerNorm over the last dim (image_encoder.py:168,180) of fp32 x[rows, dim] -> bf16.
+ * window > 0 additionally performs window_partition (image_encoder.py:243-264): x is [B, grid, grid, dim]
+ * and y is [B * nW, window*window, dim] with zero rows where the padded window leaves the image. */
+int ullsam_op_layernorm(const float* x, const float* gamma, const float* beta, float eps, int B, int grid,
+                        int dim, int window, void* y_bf16, void* stream);
+
+/* Attention with decomposed relative position (image_encoder.py:224-240, 325-361).
+ * q,k,v: bf16 [G][heads][T][64], T = grid*grid (grid = 14 windowed, 64 global); rel_h/rel_w: fp32
+ * [2*grid-1, 64]; out: bf16 [B, 64, 64, heads*64] — for grid == 14 the kernel also undoes the window
+ * partition (window_unpartition, image_encoder.py:267-289) and drops the padded query rows. */
+int ullsam_op_attention(const void* q, const void* k, const void* v, const float* rel_h, const float* rel_w,
+                        int G, int heads, int grid, void* out_bf16, void* stream);
+
+/* PatchEmbed's im2col (image_encoder.py:387-395): images [B,3,1024,1024] (dtype) -> bf16 [B*4096, 768]. */
+int ullsam_op_im2col(const void* images, int dtype, int B, void* patches_bf16, void* stream);
+
+/* fp32 -> bf16 (count elements). */
+int ullsam_op_cast_bf16(const float* x, size_t count, void* y_bf16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ULLSAM_H_ */

@@ -1,0 +1,119 @@
+"""tcgen05 GEMM epilogues vs a plain torch fp32 computation of the same op (floating-point kernel:
+tolerance = bf16 operand rounding only, accumulation is fp32 on both sides)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(M, N, K, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    return a, w, b
+
+
+def _ref(a, w, b):
+    return a.float() @ w.float().t() + b
+
+
+def _close(got, ref, tol, what):
+    err = (got.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"{what}: max|err|={err:.3e} scale={scale:.3e}")
+    assert err <= tol * scale, f"{what}: max|err| {err} vs scale {scale}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 128), (384, 768, 768), (1000, 2304, 768),
+                                   (4900, 768, 3072), (131072 // 8, 3072, 768)])
+def test_gemm_bias_bf16(M, N, K):
+    from ullsam_b200 import _lib, ops
+
+    a, w, b = _mk(M, N, K)
+    out = ops.gemm(a, w, b, epi=_lib.EPI_BF16)
+    torch.cuda.synchronize()
+    _close(out, _ref(a, w, b), 8e-3, f"bias_bf16 {M}x{N}x{K}")
+
+
+def test_gemm_gelu_relu():
+    from ullsam_b200 import _lib, ops
+
+    a, w, b = _mk(512, 3072, 768, 1)
+    ref = _ref(a, w, b)
+    out = ops.gemm(a, w, b, epi=_lib.EPI_BF16, act=_lib.ACT_GELU)
+    _close(out, torch.nn.functional.gelu(ref), 8e-3, "gelu")
+    out = ops.gemm(a, w, b, epi=_lib.EPI_F32, act=_lib.ACT_RELU)
+    _close(out, torch.relu(ref), 1e-4, "relu_f32")
+
+
+def test_gemm_residual_inplace():
+    from ullsam_b200 import _lib, ops
+
+    a, w, b = _mk(640, 768, 3072, 2)
+    res = torch.randn(640, 768, device="cuda")
+    ref = _ref(a, w, b) + res
+    x = res.clone()
+    ops.gemm(a, w, b, epi=_lib.EPI_RES_F32, out=x, residual=x)
+    _close(x, ref, 1e-4, "residual")
+
+
+def test_gemm_patch_pos():
+    from ullsam_b200 import _lib, ops
+
+    a, w, b = _mk(8192, 768, 768, 3)
+    pos = torch.randn(4096, 768, device="cuda") * 0.02
+    out = ops.gemm(a, w, b, epi=_lib.EPI_PATCH, pos=pos)
+    ref = _ref(a, w, b) + pos.repeat(2, 1)
+    _close(out, ref, 1e-4, "patch+pos")
+
+
+@pytest.mark.parametrize("T,G", [(196, 50), (4096, 2)])
+def test_gemm_qkv_split(T, G):
+    from ullsam_b200 import _lib, ops
+
+    heads, dim = 12, 768
+    a, w, b = _mk(G * T, 3 * dim, dim, 4)
+    q = torch.zeros(G, heads, T, 64, dtype=torch.bfloat16, device="cuda")
+    k, v = torch.zeros_like(q), torch.zeros_like(q)
+    ops.gemm(a, w, b, epi=_lib.EPI_QKV, qkv=(q, k, v), T=T, heads=heads)
+    ref = _ref(a, w, b).reshape(G, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    for name, got, r in (("q", q, ref[0]), ("k", k, ref[1]), ("v", v, ref[2])):
+        _close(got, r, 8e-3, f"qkv[{name}] T={T}")
+
+
+def _ln2d(x, w, b, eps):
+    u = x.mean(-1, keepdim=True)
+    s = (x - u).pow(2).mean(-1, keepdim=True)
+    return (x - u) / torch.sqrt(s + eps) * w + b
+
+
+def test_gemm_neck_ln_epilogues():
+    from ullsam_b200 import _lib, ops
+
+    B = 2
+    a, w, _ = _mk(B * 4096, 256, 768, 5)
+    lw = torch.randn(256, device="cuda") * 0.2 + 1.0
+    lb = torch.randn(256, device="cuda") * 0.1
+    ref = _ln2d(a.float() @ w.float().t(), lw, lb, 1e-6)
+    out = ops.gemm(a, w, None, epi=_lib.EPI_LN_BF16, ln_w=lw, ln_b=lb, ln_eps=1e-6)
+    _close(out, ref, 1e-2, "ln_bf16")
+    out2 = ops.gemm(a, w, None, epi=_lib.EPI_LN_NCHW, ln_w=lw, ln_b=lb, ln_eps=1e-6, hw=4096)
+    _close(out2, ref.reshape(B, 4096, 256).permute(0, 2, 1), 2e-4, "ln_nchw")
+
+
+def test_gemm_conv3x3_implicit():
+    from ullsam_b200 import _lib, ops
+
+    B, Cc = 2, 256
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = (torch.randn(B, 64, 64, Cc, device="cuda", generator=g) * 0.5).bfloat16()
+    wt = (torch.randn(256, Cc, 3, 3, device="cuda", generator=g) * 0.03).bfloat16()
+    lw = torch.ones(256, device="cuda")
+    lb = torch.zeros(256, device="cuda")
+    # kernel weight layout: [out][ (ky*3+kx)*C + c ]
+    wk = wt.permute(0, 2, 3, 1).reshape(256, 9 * Cc).contiguous()
+    conv = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1)  # [B,256,64,64]
+    ref = _ln2d(conv.permute(0, 2, 3, 1), lw, lb, 1e-6).permute(0, 3, 1, 2).reshape(B, 256, 4096)
+    out = ops.gemm(x, wk, None, epi=_lib.EPI_LN_NCHW, ln_w=lw, ln_b=lb, ln_eps=1e-6, hw=4096, conv3=True)
+    _close(out, ref, 2e-4, "conv3x3+ln")

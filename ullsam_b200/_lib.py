@@ -1,0 +1,166 @@
+"""ctypes binding of libullsam_b200.so (the C ABI declared in include/ullsam.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C ullsam_b200/csrc``.  There is no
+fallback: if the shared object is missing, ``load()`` raises, and every compute entry point returns
+``ULLSAM_ERR_NO_DEVICE`` on a machine without an sm_100 GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libullsam_b200.so")
+
+OK = 0
+F32, BF16, F16 = 0, 1, 2
+
+EPI_BF16, EPI_RES_F32, EPI_QKV, EPI_PATCH, EPI_LN_BF16, EPI_LN_NCHW, EPI_F32 = range(7)
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+
+class UllsamError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    """Mirror of ``ullsam_config`` (include/ullsam.h)."""
+
+    _fields_ = [
+        ("img_size", C.c_int32),
+        ("patch_size", C.c_int32),
+        ("in_chans", C.c_int32),
+        ("embed_dim", C.c_int32),
+        ("depth", C.c_int32),
+        ("num_heads", C.c_int32),
+        ("mlp_dim", C.c_int32),
+        ("out_chans", C.c_int32),
+        ("window_size", C.c_int32),
+        ("num_global", C.c_int32),
+        ("global_attn_indexes", C.c_int32 * 8),
+        ("enc_ln_eps", C.c_float),
+        ("transformer_dim", C.c_int32),
+        ("dec_depth", C.c_int32),
+        ("dec_heads", C.c_int32),
+        ("dec_mlp_dim", C.c_int32),
+        ("num_mask_tokens", C.c_int32),
+        ("iou_head_hidden", C.c_int32),
+        ("iou_head_depth", C.c_int32),
+    ]
+
+
+class GemmDesc(C.Structure):
+    """Mirror of ``ullsam_gemm_desc`` (include/ullsam.h)."""
+
+    _fields_ = [
+        ("epi", C.c_int32),
+        ("M", C.c_int32),
+        ("N", C.c_int32),
+        ("K", C.c_int32),
+        ("a_conv3", C.c_int32),
+        ("conv_c", C.c_int32),
+        ("A", C.c_void_p),
+        ("W", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("out", C.c_void_p),
+        ("ldc", C.c_int32),
+        ("act", C.c_int32),
+        ("residual", C.c_void_p),
+        ("pos", C.c_void_p),
+        ("pos_rows", C.c_int32),
+        ("q", C.c_void_p),
+        ("k", C.c_void_p),
+        ("v", C.c_void_p),
+        ("T", C.c_int32),
+        ("heads", C.c_int32),
+        ("ln_w", C.c_void_p),
+        ("ln_b", C.c_void_p),
+        ("ln_eps", C.c_float),
+        ("hw", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/ullsam.h declares.
+PROTOTYPES = {
+    "ullsam_abi_version": (C.c_int, []),
+    "ullsam_last_error": (C.c_char_p, [C.c_void_p]),
+    "ullsam_create": (C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(C.c_void_p)]),
+    "ullsam_destroy": (None, [C.c_void_p]),
+    "ullsam_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int]),
+    "ullsam_missing_weights": (C.c_int, [C.c_void_p, C.c_int]),
+    "ullsam_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "ullsam_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "ullsam_decoder_forward": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "ullsam_decoder_predict_masks": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+         C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "ullsam_transformer_forward": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "ullsam_segment_host": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+         C.c_void_p, C.c_void_p],
+    ),
+    "ullsam_op_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "ullsam_op_layernorm": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p],
+    ),
+    "ullsam_op_attention": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p],
+    ),
+    "ullsam_op_im2col": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ullsam_op_cast_bf16": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and attach the prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UllsamError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C ullsam_b200/csrc`).  There is no CPU/eager fallback for this path."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error(handle: Optional[int] = None) -> str:
+    msg = load().ullsam_last_error(C.c_void_p(handle) if handle else None)
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status: int, handle: Optional[int] = None, what: str = "") -> None:
+    if status != OK:
+        raise UllsamError(f"{what or 'ullsam call'} failed (status {status}): {last_error(handle)}")
+
+
+def ptr(t) -> Optional[int]:
+    """Device/host pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream_ptr(device=None) -> int:
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,92 @@
+// ullsam_b200 — C ABI, operator-level entry points (include/ullsam.h, "operator-level" section).
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../include/ullsam.h"
+#include "api_internal.h"
+#include "attention.h"
+#include "elementwise.h"
+#include "gemm.h"
+
+namespace ullsam {
+
+thread_local std::string g_thread_error;
+
+int fail(ullsam_handle* h, int code, const std::string& msg);  // model.cu
+
+int op_fail(int code, const char* msg) {
+  g_thread_error = msg ? msg : "unknown error";
+  return code;
+}
+
+int device_sm_count() {
+  static int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev != cached_dev) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+    if (prop.major != 10) return -1;
+    cached = prop.multiProcessorCount;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+}  // namespace ullsam
+
+using namespace ullsam;
+
+extern "C" {
+
+int ullsam_abi_version(void) { return ULLSAM_ABI_VERSION; }
+
+int ullsam_op_gemm(const ullsam_gemm_desc* d, void* stream) {
+  if (!d) return op_fail(ULLSAM_ERR_INVALID, "op_gemm: null descriptor");
+  const int sms = device_sm_count();
+  if (sms <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_gemm: no sm_100 device (no fallback path exists)");
+  GemmParams p{};
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.a_conv3 = d->a_conv3; p.conv_c = d->conv_c;
+  p.bias = d->bias; p.out = d->out; p.ldc = d->ldc; p.act = d->act;
+  p.residual = d->residual; p.pos = d->pos; p.pos_rows = d->pos_rows;
+  p.q = static_cast<__nv_bfloat16*>(d->q); p.k = static_cast<__nv_bfloat16*>(d->k); p.v = static_cast<__nv_bfloat16*>(d->v);
+  p.T = d->T; p.heads = d->heads;
+  p.ln_w = d->ln_w; p.ln_b = d->ln_b; p.ln_eps = d->ln_eps; p.hw = d->hw;
+  const char* e = launch_gemm(d->epi, d->A, d->W, p, sms, static_cast<cudaStream_t>(stream));
+  return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
+}
+
+int ullsam_op_layernorm(const float* x, const float* gamma, const float* beta, float eps, int B, int grid, int dim,
+                        int window, void* y_bf16, void* stream) {
+  if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_layernorm: no sm_100 device");
+  const char* e = launch_layernorm(x, gamma, beta, eps, B, grid, dim, window, static_cast<__nv_bfloat16*>(y_bf16),
+                                   static_cast<cudaStream_t>(stream));
+  return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
+}
+
+int ullsam_op_attention(const void* q, const void* k, const void* v, const float* rel_h, const float* rel_w, int G,
+                        int heads, int grid, void* out_bf16, void* stream) {
+  if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_attention: no sm_100 device");
+  const char* e = launch_attention(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
+                                   static_cast<const __nv_bfloat16*>(v), rel_h, rel_w, G, heads, grid,
+                                   static_cast<__nv_bfloat16*>(out_bf16), static_cast<cudaStream_t>(stream));
+  return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
+}
+
+int ullsam_op_im2col(const void* images, int dtype, int B, void* patches_bf16, void* stream) {
+  if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_im2col: no sm_100 device");
+  if (dtype != ULLSAM_F32 && dtype != ULLSAM_BF16) return op_fail(ULLSAM_ERR_INVALID, "op_im2col: dtype must be f32 or bf16");
+  const char* e = launch_im2col16(images, dtype == ULLSAM_BF16, B, 3, 1024, static_cast<__nv_bfloat16*>(patches_bf16),
+                                  static_cast<cudaStream_t>(stream));
+  return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
+}
+
+int ullsam_op_cast_bf16(const float* x, size_t count, void* y_bf16, void* stream) {
+  if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_cast_bf16: no sm_100 device");
+  const char* e = launch_cast_f32_bf16(x, count, static_cast<__nv_bfloat16*>(y_bf16), static_cast<cudaStream_t>(stream));
+  return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
+}
+
+}  // extern "C"

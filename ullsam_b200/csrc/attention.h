@@ -1,0 +1,16 @@
+// ullsam_b200 — fused attention with decomposed relative-position bias (attention.cu).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace ullsam {
+
+// q,k,v: bf16 [G][heads][T][64] with T = grid*grid; rel_h, rel_w: fp32 [2*grid-1][64].
+// out: bf16 [B][64][64][heads*64] token-major image layout.  grid == 64: G == B (global attention);
+// grid == 14: G == 25*B windows of the 5x5 partition of the zero-padded 70x70 grid, padded query
+// rows are dropped on the store (image_encoder.py:224-289, 325-361).
+const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const float* rel_h,
+                             const float* rel_w, int G, int heads, int grid, __nv_bfloat16* out, cudaStream_t stream);
+
+}  // namespace ullsam

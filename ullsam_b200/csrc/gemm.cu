@@ -1,0 +1,113 @@
+// ullsam_b200 — host side of the tcgen05 GEMM: TMA tensor-map construction and launch.
+#include "gemm.h"
+
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "gemm_sm100.cuh"
+
+namespace ullsam {
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static const char* load_encode() {
+  static std::once_flag once;
+  static const char* err = nullptr;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+      err = "cuTensorMapEncodeTiled not available from the CUDA driver";
+      return;
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  });
+  return err;
+}
+
+const char* make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                              uint32_t box_cols) {
+  if (const char* e = load_encode()) return e;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(2d) failed";
+}
+
+const char* make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t box_c,
+                                uint32_t box_w, uint32_t box_h) {
+  if (const char* e = load_encode()) return e;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(4d) failed";
+}
+
+template <int BN, int EPI>
+static const char* launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
+                            cudaStream_t stream) {
+  using L = GemmSmem<BN>;
+  static bool configured = false;
+  auto kern = gemm_kernel<BN, EPI>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    configured = true;
+  }
+  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * (p.N / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, GEMM_THREADS, L::kTotal, stream>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  if (p.M <= 0) return nullptr;
+  if (p.K % GEMM_BK != 0) return "gemm: K must be a multiple of 64";
+  const bool ln = (epi == EPI_LN_BF16 || epi == EPI_LN_NCHW);
+  int bn = (p.N % 256 == 0) ? 256 : 128;
+  if (p.N % bn != 0) return "gemm: N must be a multiple of 128";
+  if (ln && p.N != 256) return "gemm: LayerNorm2d epilogue needs N == 256";
+  CUtensorMap ta, tb;
+  const char* e;
+  if (p.a_conv3) {
+    if (p.M % (64 * 64) != 0) return "gemm: conv3x3 mode needs whole 64x64 images";
+    e = make_tmap_nhwc_bf16(&ta, A, p.M / 4096, 64, 64, p.conv_c, 64, 64, 2);
+  } else {
+    e = make_tmap_2d_bf16(&ta, A, (uint64_t)p.M, (uint64_t)p.K, GEMM_BM, GEMM_BK);
+  }
+  if (e) return e;
+  e = make_tmap_2d_bf16(&tb, W, (uint64_t)p.N, (uint64_t)p.K, bn, GEMM_BK);
+  if (e) return e;
+
+#define ULLSAM_GEMM_CASE(EPI)                                                            \
+  case EPI:                                                                              \
+    return bn == 256 ? launch_t<256, EPI>(ta, tb, p, num_sms, stream)                    \
+                     : launch_t<128, EPI>(ta, tb, p, num_sms, stream);
+  switch (epi) {
+    ULLSAM_GEMM_CASE(EPI_BF16)
+    ULLSAM_GEMM_CASE(EPI_RES_F32)
+    ULLSAM_GEMM_CASE(EPI_QKV)
+    ULLSAM_GEMM_CASE(EPI_PATCH)
+    ULLSAM_GEMM_CASE(EPI_F32)
+    case EPI_LN_BF16:
+      return launch_t<256, EPI_LN_BF16>(ta, tb, p, num_sms, stream);
+    case EPI_LN_NCHW:
+      return launch_t<256, EPI_LN_NCHW>(ta, tb, p, num_sms, stream);
+    default:
+      return "gemm: unknown epilogue";
+  }
+#undef ULLSAM_GEMM_CASE
+}
+
+}  // namespace ullsam

@@ -1,0 +1,53 @@
+// ullsam_b200 — host-visible declarations of the tcgen05 GEMM (see gemm_sm100.cuh for the kernel).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ullsam {
+
+enum EpiMode : int {
+  EPI_BF16 = 0,     // out bf16 [M,ldc] = act(acc + bias)
+  EPI_RES_F32 = 1,  // out fp32 [M,ldc] = acc + bias + residual[M,ldc]      (image_encoder.py:179-180)
+  EPI_QKV = 2,      // q/k/v bf16 [G][heads][T][64] <- acc + bias            (image_encoder.py:227-229)
+  EPI_PATCH = 3,    // out fp32 = acc + bias + pos[row % pos_rows][n]       (image_encoder.py:107-109)
+  EPI_LN_BF16 = 4,  // LayerNorm2d over the N == BN channels -> bf16 NHWC    (common.py:31-43)
+  EPI_LN_NCHW = 5,  // LayerNorm2d -> fp32 [B][N][hw]                       (image_encoder.py:114)
+  EPI_F32 = 6,      // out fp32 [M,ldc] = act(acc + bias)
+};
+
+enum ActMode : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+struct GemmParams {
+  int M, N, K;        // K = reduction length (conv3x3: 9 * C)
+  int a_conv3;        // 0: A is a plain [M,K] matrix; 1: implicit 3x3/pad-1 conv over NHWC [B,64,64,C]
+  int conv_c;         // channels of the conv input
+  const float* bias;  // [N] or nullptr
+  void* out;
+  int ldc;
+  int act;
+  const float* residual;
+  const float* pos;
+  int pos_rows;
+  __nv_bfloat16* q;
+  __nv_bfloat16* k;
+  __nv_bfloat16* v;
+  int T;      // rows per attention group (196 windowed, 4096 global)
+  int heads;  // attention heads; model dim = heads*64
+  const float* ln_w;
+  const float* ln_b;
+  float ln_eps;
+  int hw;  // tokens per image for the NCHW store
+};
+
+// All return nullptr on success or a static error string.
+const char* make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                              uint32_t box_cols);
+const char* make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t box_c,
+                                uint32_t box_w, uint32_t box_h);
+// A: bf16 [M,K] row-major (or NHWC [B,64,64,C] when p.a_conv3); W: bf16 [N,K] row-major.
+const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams& p, int num_sms, cudaStream_t stream);
+
+}  // namespace ullsam

@@ -1,0 +1,310 @@
+// ullsam_b200 — persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = A[M,K] (bf16, K-major) x W[N,K]^T (bf16, K-major, i.e. an nn.Linear weight as stored)
+//
+// One CTA per SM, static tile scheduler (tile = blockIdx.x + i*gridDim.x, N fastest).
+//   warp 0      : TMA producer  (A and W tiles, 128-byte swizzle, NSTAGE-deep mbarrier ring)
+//   warp 1      : MMA issuer    (one elected lane, tcgen05.mma cta_group::1, 128 x BN x 16)
+//   warp 2      : TMEM allocator
+//   warps 4..11 : epilogue      (tcgen05.ld 32x32b.x32; thread == accumulator row; two warps per
+//                                TMEM lane quadrant split the BN columns between them)
+// The fp32 accumulator lives in TMEM and is double-buffered (2 x BN columns) so the epilogue of
+// tile i overlaps the main loop of tile i+1.
+//
+// The epilogue is a compile-time policy (EPI_*) — this is where LayerNorm2d, GELU, residual adds,
+// the q/k/v head split and the NCHW transpose of the reference's modules are fused.
+#pragma once
+
+#include "common.cuh"
+#include "gemm.h"
+
+namespace ullsam {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_WARP0 = 4;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
+  static constexpr int kBBytes = BN * GEMM_BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem ptr, LN scratch (2 x 2 x 128 floats)
+  static constexpr int kScratchOffset = kBarOffset + (2 * kStages + 4) * 8 + 16;
+  static constexpr int kTotal = kScratchOffset + 4 * 128 * 4 + 1024 /* alignment slack */;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using L = GemmSmem<BN>;
+  constexpr int S = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull_bar = empty_bar + S;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* scratch = reinterpret_cast<float*>(smem + L::kScratchOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_n = p.N / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = p.K / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          if (p.a_conv3) {
+            const int cblocks = p.conv_c / GEMM_BK;
+            const int tap = kb / cblocks, cb = kb % cblocks;
+            const int dy = tap / 3, dx = tap % 3;
+            const int b = m_blk / 32, y0 = (m_blk % 32) * 2;
+            tma_load_4d(sa, &tmA, &full_bar[stage], cb * GEMM_BK, dx - 1, y0 + dy - 1, b);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+          }
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
+            umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else if (warp >= GEMM_EPI_WARP0) {
+    // ================================ epilogue ====================================
+    const int quad = warp & 3;
+    const int half = (warp - GEMM_EPI_WARP0) >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int NCHUNK = COLS_PER_WARP / 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * GEMM_BM + row_in_tile;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * COLS_PER_WARP;
+      const int col0 = n_blk * BN + half * COLS_PER_WARP;
+
+      if constexpr (EPI == EPI_LN_BF16 || EPI == EPI_LN_NCHW) {
+        // ---- LayerNorm2d across the BN (== N) channels of this token; two warps share a row ----
+        float* s_sum = scratch;             // [2][128]
+        float* s_sq = scratch + 2 * 128;    // [2][128]
+        float part = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr0 + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) part += __uint_as_float(v[j]);
+        }
+        s_sum[half * 128 + row_in_tile] = part;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float mean = (s_sum[row_in_tile] + s_sum[128 + row_in_tile]) * (1.0f / BN);
+        part = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr0 + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = __uint_as_float(v[j]) - mean;
+            part += d * d;
+          }
+        }
+        s_sq[half * 128 + row_in_tile] = part;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float var = (s_sq[row_in_tile] + s_sq[128 + row_in_tile]) * (1.0f / BN);
+        const float rstd = 1.0f / sqrtf(var + p.ln_eps);
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr0 + c * 32, v);
+          tmem_wait_ld();
+          const int n0 = col0 + c * 32;
+          if constexpr (EPI == EPI_LN_BF16) {
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = (__uint_as_float(v[2 * j]) - mean) * rstd * __ldg(p.ln_w + n0 + 2 * j) + __ldg(p.ln_b + n0 + 2 * j);
+              const float b = (__uint_as_float(v[2 * j + 1]) - mean) * rstd * __ldg(p.ln_w + n0 + 2 * j + 1) + __ldg(p.ln_b + n0 + 2 * j + 1);
+              o[j] = pack_bf16(a, b);
+            }
+            if (row_ok) {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldc + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+          } else {
+            // NCHW: out[b][n][pix]; consecutive lanes hold consecutive pixels -> coalesced per channel
+            if (row_ok) {
+              const int b = row / p.hw, pix = row % p.hw;
+              float* dst = reinterpret_cast<float*>(p.out) + (static_cast<size_t>(b) * p.N + n0) * p.hw + pix;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                dst[static_cast<size_t>(j) * p.hw] =
+                    (__uint_as_float(v[j]) - mean) * rstd * __ldg(p.ln_w + n0 + j) + __ldg(p.ln_b + n0 + j);
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr0 + c * 32, v);
+          tmem_wait_ld();
+          const int n0 = col0 + c * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+          }
+          if constexpr (EPI == EPI_BF16 || EPI == EPI_F32) {
+            if (p.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            } else if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+          }
+          if (!row_ok) continue;
+          if constexpr (EPI == EPI_BF16) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                  pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+          } else if constexpr (EPI == EPI_F32) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else if constexpr (EPI == EPI_RES_F32) {
+            const float4* res = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(row) * p.ldc + n0);
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r = res[j];
+              dst[j] = make_float4(f[4 * j] + r.x, f[4 * j + 1] + r.y, f[4 * j + 2] + r.z, f[4 * j + 3] + r.w);
+            }
+          } else if constexpr (EPI == EPI_PATCH) {
+            const float4* pos = reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(row % p.pos_rows) * p.N + n0);
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r = __ldg(pos + j);
+              dst[j] = make_float4(f[4 * j] + r.x, f[4 * j + 1] + r.y, f[4 * j + 2] + r.z, f[4 * j + 3] + r.w);
+            }
+          } else if constexpr (EPI == EPI_QKV) {
+            const int dim = p.heads * 64;
+            const int which = n0 / dim;
+            const int rem = n0 - which * dim;
+            const int head = rem >> 6, d0 = rem & 63;
+            const int g = row / p.T, t = row - g * p.T;
+            __nv_bfloat16* base = which == 0 ? p.q : (which == 1 ? p.k : p.v);
+            uint4* dst = reinterpret_cast<uint4*>(base + ((static_cast<size_t>(g) * p.heads + head) * p.T + t) * 64 + d0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                  pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+          }
+        }
+      }
+      // release this accumulator buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace ullsam

@@ -1,0 +1,130 @@
+"""Operator-level wrappers over the C ABI (``ullsam_op_*``) taking CUDA torch tensors.
+
+These are what the kernel parity tests call; the nn.Module shims in ``ullsam_b200.modeling`` use the
+model-level entry points instead.  torch is only the allocator / stream provider here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, check, current_stream_ptr, ptr
+
+
+def _require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.UllsamError("ullsam_b200 ops need CUDA tensors; there is no CPU path")
+
+
+def gemm(
+    a: torch.Tensor,
+    w: torch.Tensor,
+    bias: Optional[torch.Tensor] = None,
+    *,
+    epi: int = _lib.EPI_BF16,
+    act: int = _lib.ACT_NONE,
+    out: Optional[torch.Tensor] = None,
+    residual: Optional[torch.Tensor] = None,
+    pos: Optional[torch.Tensor] = None,
+    qkv: Optional[tuple] = None,
+    T: int = 0,
+    heads: int = 0,
+    ln_w: Optional[torch.Tensor] = None,
+    ln_b: Optional[torch.Tensor] = None,
+    ln_eps: float = 1e-6,
+    hw: int = 4096,
+    conv3: bool = False,
+) -> Optional[torch.Tensor]:
+    """C = A[M,K] @ W[N,K]^T with the epilogue selected by ``epi`` (see include/ullsam.h)."""
+    _require_cuda(a, w, bias, out, residual, pos, ln_w, ln_b)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
+    N, K = w.shape
+    if conv3:
+        B, H, Wd, Cc = a.shape
+        M = B * H * Wd
+        assert K == 9 * Cc
+    else:
+        M = a.shape[0]
+        assert a.shape[1] == K
+    d = GemmDesc()
+    d.epi, d.M, d.N, d.K = epi, M, N, K
+    d.a_conv3, d.conv_c = (1, a.shape[-1]) if conv3 else (0, 0)
+    d.A, d.W, d.bias = ptr(a), ptr(w), ptr(bias)
+    d.act = act
+    d.ldc = N
+    if epi == _lib.EPI_QKV:
+        q, k, v = qkv
+        d.q, d.k, d.v, d.T, d.heads = ptr(q), ptr(k), ptr(v), T, heads
+    else:
+        if out is None:
+            if epi in (_lib.EPI_BF16, _lib.EPI_LN_BF16):
+                out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+            elif epi == _lib.EPI_LN_NCHW:
+                out = torch.empty((M // hw, N, hw), dtype=torch.float32, device=a.device)
+            else:
+                out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+        d.out = ptr(out)
+    d.residual = ptr(residual)
+    d.pos = ptr(pos)
+    d.pos_rows = pos.shape[0] if pos is not None else 0
+    d.ln_w, d.ln_b, d.ln_eps, d.hw = ptr(ln_w), ptr(ln_b), ln_eps, hw
+    check(_lib.load().ullsam_op_gemm(C.byref(d), current_stream_ptr(a.device)), what="ullsam_op_gemm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, window: int = 0) -> torch.Tensor:
+    """x fp32 [B, grid, grid, dim] -> bf16 LayerNorm; ``window`` > 0 also window-partitions (zero pad rows)."""
+    _require_cuda(x, gamma, beta)
+    B, g, g2, dim = x.shape
+    assert g == g2 and x.dtype == torch.float32 and x.is_contiguous()
+    if window > 0:
+        nwin = -(-g // window)
+        y = torch.empty((B * nwin * nwin, window * window, dim), dtype=torch.bfloat16, device=x.device)
+    else:
+        y = torch.empty((B, g, g, dim), dtype=torch.bfloat16, device=x.device)
+    check(
+        _lib.load().ullsam_op_layernorm(ptr(x), ptr(gamma), ptr(beta), eps, B, g, dim, window, ptr(y),
+                                        current_stream_ptr(x.device)),
+        what="ullsam_op_layernorm",
+    )
+    return y
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor,
+              grid: int) -> torch.Tensor:
+    """q,k,v bf16 [G, heads, grid*grid, 64] -> bf16 [B, 64, 64, heads*64] (windows merged when grid == 14)."""
+    _require_cuda(q, k, v, rel_h, rel_w)
+    G, heads, T, hd = q.shape
+    assert hd == 64 and T == grid * grid and q.dtype == torch.bfloat16
+    B = G if grid == 64 else G // 25
+    out = torch.empty((B, 64, 64, heads * 64), dtype=torch.bfloat16, device=q.device)
+    check(
+        _lib.load().ullsam_op_attention(ptr(q), ptr(k), ptr(v), ptr(rel_h), ptr(rel_w), G, heads, grid, ptr(out),
+                                        current_stream_ptr(q.device)),
+        what="ullsam_op_attention",
+    )
+    return out
+
+
+def im2col(images: torch.Tensor) -> torch.Tensor:
+    _require_cuda(images)
+    B = images.shape[0]
+    assert images.shape[1:] == (3, 1024, 1024) and images.is_contiguous()
+    dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}[images.dtype]
+    out = torch.empty((B * 4096, 768), dtype=torch.bfloat16, device=images.device)
+    check(_lib.load().ullsam_op_im2col(ptr(images), dt, B, ptr(out), current_stream_ptr(images.device)),
+          what="ullsam_op_im2col")
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().ullsam_op_cast_bf16(ptr(x), x.numel(), ptr(y), current_stream_ptr(x.device)),
+          what="ullsam_op_cast_bf16")
+    return y
