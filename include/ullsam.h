@@ -162,10 +162,10 @@ int ullsam_op_layernorm(const float* x, const float* gamma, const float* beta, f
                         int dim, int window, void* y_bf16, void* stream);
 
 /* Attention with decomposed relative position (image_encoder.py:224-240, 325-361).
- * q,k,v: bf16 [G][heads][T][64], T = grid*grid (grid = 14 windowed, 64 global); rel_h/rel_w: fp32
- * [2*grid-1, 64]; out: bf16 [B, 64, 64, heads*64] — for grid == 14 the kernel also undoes the window
+ * q,k,v: bf16 [G][heads][T][64], T = grid*grid (grid = 14 windowed, 64 global); rel_h/rel_w: bf16
+ * [NREL, 64] = rel_pos_h / rel_pos_w ([2*grid-1, 64]) zero-padded to NREL = 128 (grid 64) / 32 (grid 14) rows; out: bf16 [B, 64, 64, heads*64] — for grid == 14 the kernel also undoes the window
  * partition (window_unpartition, image_encoder.py:267-289) and drops the padded query rows. */
-int ullsam_op_attention(const void* q, const void* k, const void* v, const float* rel_h, const float* rel_w,
+int ullsam_op_attention(const void* q, const void* k, const void* v, const void* rel_h, const void* rel_w,
                         int G, int heads, int grid, void* out_bf16, void* stream);
 
 /* PatchEmbed's im2col (image_encoder.py:387-395): images [B,3,1024,1024] (dtype) -> bf16 [B*4096, 768]. */

@@ -66,11 +66,12 @@ int ullsam_op_layernorm(const float* x, const float* gamma, const float* beta, f
   return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
 }
 
-int ullsam_op_attention(const void* q, const void* k, const void* v, const float* rel_h, const float* rel_w, int G,
+int ullsam_op_attention(const void* q, const void* k, const void* v, const void* rel_h, const void* rel_w, int G,
                         int heads, int grid, void* out_bf16, void* stream) {
   if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_attention: no sm_100 device");
   const char* e = launch_attention(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
-                                   static_cast<const __nv_bfloat16*>(v), rel_h, rel_w, G, heads, grid,
+                                   static_cast<const __nv_bfloat16*>(v), static_cast<const __nv_bfloat16*>(rel_h),
+                                   static_cast<const __nv_bfloat16*>(rel_w), G, heads, grid,
                                    static_cast<__nv_bfloat16*>(out_bf16), static_cast<cudaStream_t>(stream));
   return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
 }

@@ -6,11 +6,12 @@
 
 namespace ullsam {
 
-// q,k,v: bf16 [G][heads][T][64] with T = grid*grid; rel_h, rel_w: fp32 [2*grid-1][64].
+// q,k,v: bf16 [G][heads][T][64] with T = grid*grid; rel_h, rel_w: bf16 [NREL][64], the module's
+// rel_pos_h / rel_pos_w ([2*grid-1][64]) zero-padded to NREL = 128 (grid 64) or 32 (grid 14) rows.
 // out: bf16 [B][64][64][heads*64] token-major image layout.  grid == 64: G == B (global attention);
 // grid == 14: G == 25*B windows of the 5x5 partition of the zero-padded 70x70 grid, padded query
 // rows are dropped on the store (image_encoder.py:224-289, 325-361).
-const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const float* rel_h,
-                             const float* rel_w, int G, int heads, int grid, __nv_bfloat16* out, cudaStream_t stream);
+const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                             const __nv_bfloat16* rel_h, const __nv_bfloat16* rel_w, int G, int heads, int grid, __nv_bfloat16* out, cudaStream_t stream);
 
 }  // namespace ullsam

@@ -94,16 +94,27 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return y
 
 
+def pad_rel_table(rel: torch.Tensor, grid: int) -> torch.Tensor:
+    """rel_pos_h / rel_pos_w fp32 [2*grid-1, 64] -> the kernel's bf16 table, zero-padded to 128 / 32 rows."""
+    nrel = 128 if grid == 64 else 32
+    out = torch.zeros((nrel, 64), dtype=torch.bfloat16, device=rel.device)
+    out[: rel.shape[0]] = rel.to(torch.bfloat16)
+    return out
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor,
               grid: int) -> torch.Tensor:
-    """q,k,v bf16 [G, heads, grid*grid, 64] -> bf16 [B, 64, 64, heads*64] (windows merged when grid == 14)."""
+    """q,k,v bf16 [G, heads, grid*grid, 64]; rel_h/rel_w fp32 [2*grid-1, 64] (the module parameters).
+    Returns bf16 [B, 64, 64, heads*64] (windows merged and padding dropped when grid == 14)."""
     _require_cuda(q, k, v, rel_h, rel_w)
     G, heads, T, hd = q.shape
     assert hd == 64 and T == grid * grid and q.dtype == torch.bfloat16
+    assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
     B = G if grid == 64 else G // 25
-    out = torch.empty((B, 64, 64, heads * 64), dtype=torch.bfloat16, device=q.device)
+    rh, rw = pad_rel_table(rel_h, grid), pad_rel_table(rel_w, grid)
+    out = torch.zeros((B, 64, 64, heads * 64), dtype=torch.bfloat16, device=q.device)
     check(
-        _lib.load().ullsam_op_attention(ptr(q), ptr(k), ptr(v), ptr(rel_h), ptr(rel_w), G, heads, grid, ptr(out),
+        _lib.load().ullsam_op_attention(ptr(q), ptr(k), ptr(v), ptr(rh), ptr(rw), G, heads, grid, ptr(out),
                                         current_stream_ptr(q.device)),
         what="ullsam_op_attention",
     )
