@@ -1,0 +1,179 @@
+"""End-to-end parity of the CUDA path (through the C ABI) against the CPU oracle and the committed reference goldens.
+
+Bars: image embeddings within 1e-2 relative L2 error of the fp32 reference; binarised masks
+(threshold 0.0, sam.py:19,123) with IoU >= 0.99 against the fp32 reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sam_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+def mask_iou(a, b):
+    a, b = a > 0, b > 0
+    inter = (a & b).sum().item()
+    union = (a | b).sum().item()
+    return 1.0 if union == 0 else inter / union
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from ullsam_b200.engine import Engine
+
+    cfg = O.config("vit_b")
+    g = np.load(os.path.join(GOLD, "vit_b.npz"))
+    seed = int(g["seed"])
+    sd = synth.make_state_dict(cfg, seed)
+    eng = Engine(model="vit_b")
+    n = eng.load_state_dict(sd)
+    assert eng.missing(0) == 0 and eng.missing(1) == 0, (n, eng.missing(0), eng.missing(1))
+    images, boxes = synth.make_images(2, 1024, seed=seed + 1)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        stages = {}
+        emb_ref = O.encoder_forward(sd, images, cfg, stages=stages)
+    emb = eng.encoder_forward(images.cuda())
+    torch.cuda.synchronize()
+    return dict(cfg=cfg, g=g, seed=seed, sd=sd, eng=eng, images=images, boxes=boxes, emb_ref=emb_ref, emb=emb,
+                stages=stages)
+
+
+def test_encoder_vs_oracle(ctx):
+    emb, ref = ctx["emb"].cpu(), ctx["emb_ref"]
+    assert emb.shape == (2, 256, 64, 64) and torch.isfinite(emb).all()
+    for i in range(2):
+        e = rel_l2(emb[i], ref[i])
+        print(f"image {i}: embedding rel-L2 error {e:.3e}, max|err| {(emb[i] - ref[i]).abs().max().item():.3e}")
+        assert e <= 1e-2
+
+
+def test_encoder_vs_reference_golden(ctx):
+    g = ctx["g"]
+    es = int(g["emb_stride"])
+    got = ctx["emb"][0:1, :, ::es, ::es].cpu()
+    ref = torch.from_numpy(g["emb"])
+    e = rel_l2(got, ref)
+    print(f"golden sub-sampled embedding rel-L2 error {e:.3e}")
+    assert e <= 1e-2
+
+
+def test_encoder_bf16_io(ctx):
+    eng = ctx["eng"]
+    out = eng.encoder_forward(ctx["images"][:1].cuda().bfloat16(), out_dtype=torch.bfloat16)
+    e = rel_l2(out.float().cpu()[0], ctx["emb_ref"][0])
+    print(f"bf16 in/out embedding rel-L2 error {e:.3e}")
+    assert out.dtype == torch.bfloat16 and e <= 1.5e-2
+
+
+@pytest.mark.parametrize("multimask", [False, True])
+def test_decoder_box_prompt_vs_oracle(ctx, multimask):
+    """Same embeddings on both sides (the oracle's), so this isolates the decoder."""
+    cfg, sd, eng = ctx["cfg"], ctx["sd"], ctx["eng"]
+    pe = O.dense_pe(sd, cfg)
+    sparse = O.embed_boxes(sd, ctx["boxes"], cfg)
+    dense = O.dense_no_mask(sd, 1, cfg)
+    with torch.no_grad():
+        ref_m, ref_s = [], []
+        for i in range(2):
+            m, s = O.decoder_forward(sd, ctx["emb_ref"][i:i + 1], pe, sparse[i:i + 1], dense, multimask, cfg)
+            ref_m.append(m)
+            ref_s.append(s)
+    ref_m, ref_s = torch.cat(ref_m), torch.cat(ref_s)
+    masks, iou = eng.decoder_forward(ctx["emb_ref"].cuda(), pe.cuda(), sparse.cuda(), dense.cuda(), multimask,
+                                     prompts_per_image=1)
+    masks, iou = masks.cpu(), iou.cpu()
+    assert masks.shape == ref_m.shape and iou.shape == ref_s.shape
+    for i in range(2):
+        v = mask_iou(masks[i], ref_m[i])
+        print(f"multimask={multimask} image {i}: IoU {v:.4f}, max|logit err| {(masks[i] - ref_m[i]).abs().max().item():.3e}, "
+              f"logit scale {ref_m[i].abs().max().item():.3e}, iou-head err {(iou[i] - ref_s[i]).abs().max().item():.3e}")
+        assert v >= 0.99
+        assert (iou[i] - ref_s[i]).abs().max().item() <= 2e-2 * max(1.0, ref_s[i].abs().max().item())
+
+
+def test_end_to_end_masks_vs_oracle(ctx):
+    """CUDA encoder -> CUDA decoder against oracle encoder -> oracle decoder (the headline parity bar)."""
+    cfg, sd, eng = ctx["cfg"], ctx["sd"], ctx["eng"]
+    pe = O.dense_pe(sd, cfg)
+    sparse = O.embed_boxes(sd, ctx["boxes"], cfg)
+    dense = O.dense_no_mask(sd, 1, cfg)
+    with torch.no_grad():
+        ref = torch.cat([O.decoder_forward(sd, ctx["emb_ref"][i:i + 1], pe, sparse[i:i + 1], dense, False, cfg)[0]
+                         for i in range(2)])
+    masks, _ = eng.decoder_forward(ctx["emb"], pe.cuda(), sparse.cuda(), dense.cuda(), False, prompts_per_image=1)
+    for i in range(2):
+        v = mask_iou(masks[i].cpu(), ref[i])
+        print(f"end-to-end image {i}: mask IoU {v:.4f}")
+        assert v >= 0.99
+
+
+def test_llm_conditioned_prompts_vs_reference_golden(ctx):
+    """uLLSAM convention: one image, P=3 point-prompt instances, LLM-derived dense prompt (golden = reference modules)."""
+    cfg, sd, eng, g, seed = ctx["cfg"], ctx["sd"], ctx["eng"], ctx["g"], ctx["seed"]
+    P = g["llm_masks"].shape[0]
+    coords, labels = synth.make_points(P, 1024, seed=seed + 2)
+    llm = synth.make_llm_map(1, seed=seed + 3).repeat(P, 1, 1, 1)
+    sparse = O.embed_points(sd, coords, labels, cfg, pad=True)
+    dense = O.dense_from_llm(sd, llm)
+    pe = O.dense_pe(sd, cfg)
+    masks, iou = eng.decoder_forward(ctx["emb_ref"][0:1].cuda(), pe.cuda(), sparse.cuda(), dense.cuda(), False)
+    ms = int(g["mask_stride"])
+    ref = torch.from_numpy(g["llm_masks"])
+    got = masks.cpu()[:, :, ::ms, ::ms]
+    v = mask_iou(got, ref)
+    print(f"LLM-conditioned: IoU (sub-sampled) {v:.4f}, max|err| {(got - ref).abs().max().item():.3e}")
+    assert v >= 0.99
+    assert (iou.cpu() - torch.from_numpy(g["llm_iou"])).abs().max().item() <= 2e-2
+    # predict_masks: all four masks; channel 0 must equal the single-mask output
+    m4, s4 = eng.decoder_forward(ctx["emb_ref"][0:1].cuda(), pe.cuda(), sparse.cuda(), dense.cuda(), None)
+    assert m4.shape == (P, 4, 256, 256) and torch.equal(m4[:, 0:1], masks)
+    # TwoWayTransformer alone
+    tokens = torch.cat([torch.cat([sd["mask_decoder.iou_token.weight"], sd["mask_decoder.mask_tokens.weight"]])[None]
+                        .expand(P, -1, -1), sparse], dim=1)
+    src = ctx["emb_ref"][0:1].repeat_interleave(P, 0) + dense
+    q, k = eng.transformer_forward(src.cuda(), pe.cuda(), tokens.cuda())
+    eq = (q.cpu() - torch.from_numpy(g["llm_queries"])).abs().max().item()
+    ek = (k.cpu()[:, ::64] - torch.from_numpy(g["llm_keys"])).abs().max().item()
+    print(f"transformer: queries max|err| {eq:.3e}, keys max|err| {ek:.3e}")
+    assert eq <= 5e-2 and ek <= 5e-2
+
+
+def test_segment_host_matches_device_path(ctx):
+    cfg, sd, eng = ctx["cfg"], ctx["sd"], ctx["eng"]
+    pe = O.dense_pe(sd, cfg)[0].contiguous()
+    sparse = O.embed_boxes(sd, ctx["boxes"], cfg).contiguous()
+    dvec = sd["prompt_encoder.no_mask_embed.weight"].reshape(256).contiguous()
+    masks = torch.empty(2, 1, 256, 256).pin_memory()
+    iou = torch.empty(2, 1).pin_memory()
+    emb = torch.empty(2, 256, 64, 64).pin_memory()
+    eng.segment_host(ctx["images"].pin_memory(), pe, sparse, dvec, False, masks, iou, emb)
+    assert torch.equal(emb, ctx["emb"].cpu())
+    m2, _ = eng.decoder_forward(ctx["emb"], pe[None].cuda(), sparse.cuda(), O.dense_no_mask(sd, 1, cfg).cuda(), False,
+                                prompts_per_image=1)
+    assert torch.equal(masks, m2.cpu())
+
+
+def test_errors_are_loud(ctx):
+    from ullsam_b200 import _lib
+    from ullsam_b200.engine import Engine
+
+    eng = Engine(model="vit_b")  # no weights loaded
+    with pytest.raises(_lib.UllsamError, match="not loaded"):
+        eng.encoder_forward(torch.zeros(1, 3, 1024, 1024, device="cuda"))
+    with pytest.raises(_lib.UllsamError, match="unknown state_dict key"):
+        eng.set_weight("image_encoder.nope", torch.zeros(1))
+    with pytest.raises(_lib.UllsamError, match="shape mismatch"):
+        eng.set_weight("image_encoder.patch_embed.proj.bias", torch.zeros(5))
+    with pytest.raises(_lib.UllsamError):
+        ctx["eng"].encoder_forward(torch.zeros(1, 3, 1024, 1024))  # CPU tensor: no CPU path
+    eng.close()

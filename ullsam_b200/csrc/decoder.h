@@ -1,0 +1,43 @@
+// ullsam_b200 — launchers of the prompt-token side of the mask decoder (decoder.cu).
+// Every launcher returns nullptr on success or a static error string.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace ullsam {
+
+// Y[g][m][n] = act((X[g][m][:] (+ X2[g][m][:])) . W[g][n][:] + b[g][n]) (+ res[g][m][n]);  fp32, small M.
+struct TokLinear {
+  const float* x;    // [G][M] rows of K, row stride ldx, group stride x_gs
+  const float* x2;   // optional addend with x's layout (the "+ query_pe" of transformer.py:160,166,178)
+  const float* w;    // [G][N][K], group stride w_gs
+  const float* b;    // [G][N] or nullptr, group stride b_gs
+  const float* res;  // optional residual with y's layout
+  float* y;          // row stride ldy, group stride y_gs
+  int M, N, K, G;
+  int ldx, ldy;
+  size_t x_gs, w_gs, b_gs, y_gs;
+  int act;  // 0 none, 2 ReLU
+};
+
+const char* launch_tok_linear(const TokLinear& a, cudaStream_t stream);
+const char* launch_tok_self_attn(const float* q, const float* k, const float* v, int R, int Nt, float* out,
+                                 cudaStream_t stream);
+const char* launch_tok_ln(const float* x, const float* gamma, const float* beta, int rows, float eps, float* y,
+                          cudaStream_t stream);
+// q fp32 [R][Nt][128]; kv bf16 [R*4096][ldkv] (K = cols 0..127, V = cols 128..255); S scratch fp32 [R][8][Nt][4096]
+const char* launch_t2i_attention(const float* q, const __nv_bfloat16* kv, int ldkv, int R, int Nt, float* S, float* o,
+                                 cudaStream_t stream);
+// proj bf16 [R*4096][ldp] with the image-side queries at column q_col; k, v fp32 [R][Nt][128]; out bf16 [R*4096][128]
+const char* launch_i2t_attention(const __nv_bfloat16* proj, int ldp, int q_col, const float* k, const float* v, int R,
+                                 int Nt, __nv_bfloat16* out, cudaStream_t stream);
+// keys[r][pix][c] = emb[r / P][c][pix] + dense (dense_mode 0: [dense_batch][256][4096]; 1: [dense_batch][256]; null: none)
+const char* launch_keys_init(const float* emb, int R, int P, const float* dense, int dense_mode, int dense_batch,
+                             float* keys_f32, __nv_bfloat16* keys_bf16, cudaStream_t stream);
+const char* launch_tok_init(const float* iou_token, const float* mask_tokens, int nm, const float* sparse, int Ns, int R,
+                            float* tokens, cudaStream_t stream);
+const char* launch_slice_copy(const float* in, int R, int C, int m0, int cnt, size_t inner, float* out, cudaStream_t stream);
+
+}  // namespace ullsam

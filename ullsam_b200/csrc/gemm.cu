@@ -74,10 +74,10 @@ static const char* launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const 
 const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams& p, int num_sms, cudaStream_t stream) {
   if (p.M <= 0) return nullptr;
   if (p.K % GEMM_BK != 0) return "gemm: K must be a multiple of 64";
-  const bool ln = (epi == EPI_LN_BF16 || epi == EPI_LN_NCHW);
+  const bool ln = (epi == EPI_LN_BF16 || epi == EPI_LN_NCHW || epi == EPI_LN_RES || epi == EPI_UP1);
   int bn = (p.N % 256 == 0) ? 256 : 128;
   if (p.N % bn != 0) return "gemm: N must be a multiple of 128";
-  if (ln && p.N != 256) return "gemm: LayerNorm2d epilogue needs N == 256";
+  if (ln && p.N != 256) return "gemm: this epilogue needs N == 256";
   CUtensorMap ta, tb;
   const char* e;
   if (p.a_conv3) {
@@ -100,6 +100,12 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
     ULLSAM_GEMM_CASE(EPI_QKV)
     ULLSAM_GEMM_CASE(EPI_PATCH)
     ULLSAM_GEMM_CASE(EPI_F32)
+    case EPI_LN_RES:
+      return launch_t<256, EPI_LN_RES>(ta, tb, p, num_sms, stream);
+    case EPI_UP1:
+      return launch_t<256, EPI_UP1>(ta, tb, p, num_sms, stream);
+    case EPI_MASK:
+      return p.N == 128 ? launch_t<128, EPI_MASK>(ta, tb, p, num_sms, stream) : "gemm: EPI_MASK needs N == 128";
     case EPI_LN_BF16:
       return launch_t<256, EPI_LN_BF16>(ta, tb, p, num_sms, stream);
     case EPI_LN_NCHW:

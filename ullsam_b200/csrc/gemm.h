@@ -16,7 +16,12 @@ enum EpiMode : int {
   EPI_LN_BF16 = 4,  // LayerNorm2d over the N == BN channels -> bf16 NHWC    (common.py:31-43)
   EPI_LN_NCHW = 5,  // LayerNorm2d -> fp32 [B][N][hw]                       (image_encoder.py:114)
   EPI_F32 = 6,      // out fp32 [M,ldc] = act(acc + bias)
+  EPI_LN_RES = 7,   // x = acc + bias + residual; LayerNorm(256) -> out fp32 (may alias residual) and out2 bf16
+                    //   (TwoWayAttentionBlock: keys = norm4(keys + attn_out), transformer.py:178-182)
+  EPI_UP1 = 8,      // ConvT(256->64,k2s2) + LayerNorm2d(64) + GELU -> bf16 NHWC [R,128,128,64]  (mask_decoder.py:54-56)
+  EPI_MASK = 9,     // ConvT(64->32,k2s2) + GELU, contracted with hyper_in -> mask logits         (mask_decoder.py:57-58,144)
 };
+// EPI_BF16 / EPI_F32 also add pos[row % pos_rows][n] when p.pos != nullptr.
 
 enum ActMode : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 
@@ -40,6 +45,10 @@ struct GemmParams {
   const float* ln_b;
   float ln_eps;
   int hw;  // tokens per image for the NCHW store
+  void* out2;          // EPI_LN_RES: bf16 copy of the normalised rows
+  const float* hyper;  // EPI_MASK: hyper_in [R][4][32]
+  int mask_m0;         // EPI_MASK: first mask channel written
+  int mask_cnt;        // EPI_MASK: number of mask channels written (out is [R][mask_cnt][256][256] fp32)
 };
 
 // All return nullptr on success or a static error string.

@@ -224,6 +224,133 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
+      } else if constexpr (EPI == EPI_LN_RES) {
+        // ---- x = acc + bias + residual, LayerNorm over the 256 channels (two warps share a row) ----
+        float* s_sum = scratch;
+        float* s_sq = scratch + 2 * 128;
+        const size_t rbase = static_cast<size_t>(row_ok ? row : 0) * p.ldc;
+        auto load_x = [&](int c, float (&f)[32]) {
+          uint32_t v[32];
+          tmem_ld32(taddr0 + c * 32, v);
+          tmem_wait_ld();
+          const int n0 = col0 + c * 32;
+          const float4* res = reinterpret_cast<const float4*>(p.residual + rbase + n0);
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 r = res[j];
+            const float4 b = __ldg(b4 + j);
+            f[4 * j] = __uint_as_float(v[4 * j]) + r.x + b.x;
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + r.y + b.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + r.z + b.z;
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + r.w + b.w;
+          }
+        };
+        float part = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c) {
+          float f[32];
+          load_x(c, f);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) part += f[j];
+        }
+        s_sum[half * 128 + row_in_tile] = part;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float mean = (s_sum[row_in_tile] + s_sum[128 + row_in_tile]) * (1.0f / BN);
+        part = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c) {
+          float f[32];
+          load_x(c, f);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) part += (f[j] - mean) * (f[j] - mean);
+        }
+        s_sq[half * 128 + row_in_tile] = part;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float rstd = rsqrtf((s_sq[row_in_tile] + s_sq[128 + row_in_tile]) * (1.0f / BN) + p.ln_eps);
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c) {
+          float f[32];
+          load_x(c, f);
+          const int n0 = col0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = (f[j] - mean) * rstd * __ldg(p.ln_w + n0 + j) + __ldg(p.ln_b + n0 + j);
+          if (row_ok) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + rbase + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            uint4* d2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + rbase + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              d2[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                 pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+          }
+        }
+      } else if constexpr (EPI == EPI_UP1) {
+        // ---- columns = (ky,kx,co): each 64-wide group is one output pixel; LayerNorm2d(64) + GELU ----
+        static_assert(EPI != EPI_UP1 || BN == 256, "EPI_UP1 needs BN == 256");
+        const int pr = row / 4096, pix = row % 4096;
+        const int y = pix >> 6, x = pix & 63;
+#pragma unroll 1
+        for (int gg = 0; gg < 2; ++gg) {
+          const int grp = half * 2 + gg;  // ky*2 + kx
+          float f[64];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(taddr0 + gg * 64 + c * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[c * 32 + j] = __uint_as_float(v[j]) + __ldg(p.bias + grp * 64 + c * 32 + j);
+          }
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) s += f[j];
+          const float mean = s * (1.0f / 64);
+          float sq = 0.f;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) sq += (f[j] - mean) * (f[j] - mean);
+          const float rstd = 1.0f / sqrtf(sq * (1.0f / 64) + p.ln_eps);
+          if (row_ok) {
+            const int oy = 2 * y + (grp >> 1), ox = 2 * x + (grp & 1);
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                                  ((static_cast<size_t>(pr) * 128 + oy) * 128 + ox) * 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float o[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                o[u] = gelu_erf((f[8 * j + u] - mean) * rstd * __ldg(p.ln_w + 8 * j + u) + __ldg(p.ln_b + 8 * j + u));
+              dst[j] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_MASK) {
+        // ---- rows = pixels of the 128x128 map; columns = (ky,kx,c2): GELU then contract c2 with hyper_in ----
+        static_assert(EPI != EPI_MASK || BN == 128, "EPI_MASK needs BN == 128");
+        const int pr = row / 16384, pix = row % 16384;
+        const int y = pix >> 7, x = pix & 127;
+        const float* hyp = p.hyper + static_cast<size_t>(row_ok ? pr : 0) * 4 * 32;
+#pragma unroll 1
+        for (int gg = 0; gg < 2; ++gg) {
+          const int grp = half * 2 + gg;
+          uint32_t v[32];
+          tmem_ld32(taddr0 + gg * 32, v);
+          tmem_wait_ld();
+          float u[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) u[j] = gelu_erf(__uint_as_float(v[j]) + __ldg(p.bias + grp * 32 + j));
+          if (row_ok) {
+            const int oy = 2 * y + (grp >> 1), ox = 2 * x + (grp & 1);
+            for (int m = 0; m < p.mask_cnt; ++m) {
+              const float* hm = hyp + (p.mask_m0 + m) * 32;
+              float acc = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc = fmaf(u[j], __ldg(hm + j), acc);
+              reinterpret_cast<float*>(p.out)[((static_cast<size_t>(pr) * p.mask_cnt + m) * 256 + oy) * 256 + ox] = acc;
+            }
+          }
+        }
       } else {
 #pragma unroll 1
         for (int c = 0; c < NCHUNK; ++c) {
@@ -242,6 +369,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           if constexpr (EPI == EPI_BF16 || EPI == EPI_F32) {
+            if (p.pos != nullptr) {
+              const float4* pos = reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(row % p.pos_rows) * p.N + n0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 r = __ldg(pos + j);
+                f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+              }
+            }
             if (p.act == ACT_GELU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
