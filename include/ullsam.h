@@ -128,6 +128,19 @@ int ullsam_segment_host(ullsam_handle* h, const float* images_host, int B, const
                         const float* sparse_host, int Ns, const float* dense_vec_host, int multimask,
                         float* masks_host, float* iou_host, float* emb_host /* may be NULL */);
 
+/* ---- instrumentation -------------------------------------------------------------------------- */
+
+/* Number of CUDA kernels this handle has launched since creation (bench.py's gpu_launches). */
+unsigned long long ullsam_launch_count(const ullsam_handle* h);
+
+/* Per-category device timing with CUDA events recorded on the caller's stream between launches.
+ * begin() arms it; the first marked launch after begin() is the time origin (not attributed); end()
+ * synchronises on the last event and returns milliseconds / marked-launch counts per category. */
+int ullsam_profile_begin(ullsam_handle* h);
+int ullsam_profile_end(ullsam_handle* h, float* ms_per_category, int* launches_per_category, int n);
+int ullsam_profile_categories(void);
+const char* ullsam_profile_category_name(int i);
+
 /* ---- operator-level entry points (the unit the parity tests exercise) ------------------------ */
 
 /* tcgen05 GEMM: C = A[M,K] x W[N,K]^T with a fused epilogue.  Mirrors ullsam::GemmParams. */

@@ -1,5 +1,5 @@
 """Generate tests/golden/*.npz by running the REFERENCE's own modules (imported from /root/reference, which only
-exists in the build container) on the seeded synthetic weights/inputs of oracle/synth.py.
+exists in the build container) on the seeded synthetic weights/inputs of ullsam_b200/synth.py.
 
     python -m oracle.make_golden            # writes tests/golden/{tiny,vit_b}.npz
 
@@ -49,7 +49,7 @@ def build_reference(cfg):
 @torch.no_grad()
 def run(name: str, B: int, seed: int, emb_stride: int, mask_stride: int):
     from oracle import sam_oracle as O
-    from oracle import synth
+    from ullsam_b200 import synth
 
     cfg = O.config(name)
     sd = synth.make_state_dict(cfg, seed)

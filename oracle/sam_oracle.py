@@ -15,70 +15,20 @@ the timed CPU baseline; nothing under ``ullsam_b200/`` imports it.
 
 Pinning: the reference ships no tests or golden vectors.  ``oracle/make_golden.py`` runs the
 reference's own modules (imported from /root/reference in the build container) on the seeded synthetic weights
-and inputs of ``oracle/synth.py`` and commits their outputs under ``tests/golden/``;
+and inputs of ``ullsam_b200/synth.py`` and commits their outputs under ``tests/golden/``;
 ``tests/test_oracle_golden.py`` checks this restatement against those vectors.
 """
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
 from typing import Dict, Optional, Tuple
 
 import torch
 import torch.nn.functional as F
 
+from ullsam_b200.config import SamConfig, config  # noqa: F401  (shared hyper-parameter table)
+
 SD = Dict[str, torch.Tensor]
-
-
-@dataclass
-class SamConfig:
-    """Hyper-parameters fixed by build_sam._build_sam (build_sam.py:55-98)."""
-
-    name: str = "vit_b"
-    img_size: int = 1024
-    patch_size: int = 16
-    in_chans: int = 3
-    embed_dim: int = 768
-    depth: int = 12
-    num_heads: int = 12
-    mlp_ratio: float = 4.0
-    out_chans: int = 256
-    window_size: int = 14
-    global_attn_indexes: Tuple[int, ...] = (2, 5, 8, 11)
-    enc_ln_eps: float = 1e-6
-    # decoder
-    transformer_dim: int = 256
-    dec_depth: int = 2
-    dec_heads: int = 8
-    dec_mlp_dim: int = 2048
-    num_multimask_outputs: int = 3
-    iou_head_depth: int = 3
-    iou_head_hidden_dim: int = 256
-    mask_in_chans: int = 16
-    extra: dict = field(default_factory=dict)
-
-    @property
-    def grid(self) -> int:
-        return self.img_size // self.patch_size
-
-    @property
-    def num_mask_tokens(self) -> int:
-        return self.num_multimask_outputs + 1
-
-
-def config(name: str) -> SamConfig:
-    """build_sam.py:14-44 (vit_h / vit_l / vit_b) plus a tiny configuration used to pin the oracle cheaply."""
-    if name == "vit_b":
-        return SamConfig()
-    if name == "vit_l":
-        return SamConfig(name="vit_l", embed_dim=1024, depth=24, num_heads=16, global_attn_indexes=(5, 11, 17, 23))
-    if name == "vit_h":
-        return SamConfig(name="vit_h", embed_dim=1280, depth=32, num_heads=16, global_attn_indexes=(7, 15, 23, 31))
-    if name == "tiny":
-        # 20x20 token grid: windows of 14 need padding to 28 (edge windows are partly padding), one global block.
-        return SamConfig(name="tiny", img_size=320, embed_dim=128, depth=3, num_heads=2, global_attn_indexes=(1,),
-                         out_chans=256)
-    raise KeyError(name)
 
 
 # =====================================================================================================

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import sam_oracle as O
-from oracle import synth
+from ullsam_b200 import synth
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")

@@ -110,6 +110,11 @@ PROTOTYPES = {
         [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
          C.c_void_p, C.c_void_p],
     ),
+    "ullsam_launch_count": (C.c_ulonglong, [C.c_void_p]),
+    "ullsam_profile_begin": (C.c_int, [C.c_void_p]),
+    "ullsam_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
+    "ullsam_profile_categories": (C.c_int, []),
+    "ullsam_profile_category_name": (C.c_char_p, [C.c_int]),
     "ullsam_op_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "ullsam_op_layernorm": (
         C.c_int,

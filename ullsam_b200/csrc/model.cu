@@ -111,6 +111,12 @@ struct ullsam_handle {
         *iou4 = nullptr;
   bf16 *keys_bf = nullptr, *proj = nullptr, *ao128 = nullptr, *pe_bf = nullptr, *up_h = nullptr;
   std::vector<float*> peproj;  // per layer [4096,384], final [4096,256]
+  // launch accounting + optional per-category CUDA-event profiling (ullsam_profile_*)
+  unsigned long long launches = 0;
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_cat;
+  size_t prof_n = 0;
   // host-call staging
   float *d_images = nullptr, *d_pe = nullptr, *d_sparse = nullptr, *d_dense = nullptr, *d_masks = nullptr, *d_iou = nullptr;
   int host_cap_b = 0, host_cap_ns = 0;
@@ -127,6 +133,27 @@ int fail(ullsam_handle* h, int code, const std::string& msg) {
 }  // namespace ullsam
 
 namespace {
+
+enum ProfCat : int {
+  PC_PATCH = 0, PC_LN, PC_GEMM_QKV, PC_ATTN_WIN, PC_ATTN_GLOBAL, PC_GEMM_PROJ, PC_GEMM_LIN1, PC_GEMM_LIN2, PC_NECK,
+  PC_DEC_TOKENS, PC_DEC_GEMM, PC_DEC_ATTN, PC_DEC_UPSCALE, PC_COUNT
+};
+const char* kProfNames[PC_COUNT] = {"patch_embed", "layernorm", "gemm_qkv", "attn_windowed", "attn_global", "gemm_proj",
+                                    "gemm_mlp_lin1", "gemm_mlp_lin2", "neck", "dec_token_kernels", "dec_image_gemms",
+                                    "dec_cross_attention", "dec_upscale_mask"};
+
+// called after every launch: counts kernels and, when profiling, drops a CUDA event on the stream
+void mark(ullsam_handle* h, int cat, cudaStream_t st, int nkernels = 1) {
+  h->launches += nkernels;
+  if (!h->prof_on) return;
+  if (h->prof_n == h->prof_ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    h->prof_ev.push_back(e);
+  }
+  cudaEventRecord(h->prof_ev[h->prof_n++], st);
+  h->prof_cat.push_back(cat);
+}
 
 #define CKS(expr)                                                        \
   do {                                                                   \
@@ -472,6 +499,7 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
     GemmParams p = gp(tok, D, 768);
     p.bias = h->patch_b; p.out = h->x; p.pos = h->pos; p.pos_rows = 4096;
     CKS(launch_gemm(EPI_PATCH, h->hid, h->patch_w, p, sms, st));
+    mark(h, PC_PATCH, st, 2);
   }
   for (int i = 0; i < c.depth; ++i) {
     const EncBlock& b = h->blocks[i];
@@ -479,29 +507,36 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
     const int Mq = b.global ? tok : tokw, T = b.global ? 4096 : 196;
     // norm1 (+ window_partition)
     CKS(launch_layernorm(h->x, b.ln1_w, b.ln1_b, c.enc_ln_eps, Bc, 64, D, win, h->xn, st));
+    mark(h, PC_LN, st);
     {  // qkv + head split
       GemmParams p = gp(Mq, 3 * D, D);
       p.bias = b.qkv_b; p.q = h->q; p.k = h->k; p.v = h->v; p.T = T; p.heads = heads;
       CKS(launch_gemm(EPI_QKV, h->xn, b.qkv_w, p, sms, st));
+      mark(h, PC_GEMM_QKV, st);
     }
     // attention (+ rel-pos bias, + window_unpartition)
     CKS(launch_attention(h->q, h->k, h->v, b.relh, b.relw, b.global ? Bc : Bc * 25, heads, b.global ? 64 : 14, h->ao, st));
+    mark(h, b.global ? PC_ATTN_GLOBAL : PC_ATTN_WIN, st);
     {  // proj + residual
       GemmParams p = gp(tok, D, D);
       p.bias = b.proj_b; p.out = h->x; p.residual = h->x;
       CKS(launch_gemm(EPI_RES_F32, h->ao, b.proj_w, p, sms, st));
+      mark(h, PC_GEMM_PROJ, st);
     }
     // norm2 + MLP + residual
     CKS(launch_layernorm(h->x, b.ln2_w, b.ln2_b, c.enc_ln_eps, Bc, 64, D, 0, h->xn, st));
+    mark(h, PC_LN, st);
     {
       GemmParams p = gp(tok, MD, D);
       p.bias = b.lin1_b; p.out = h->hid; p.act = ACT_GELU;
       CKS(launch_gemm(EPI_BF16, h->xn, b.lin1_w, p, sms, st));
+      mark(h, PC_GEMM_LIN1, st);
     }
     {
       GemmParams p = gp(tok, D, MD);
       p.bias = b.lin2_b; p.out = h->x; p.residual = h->x;
       CKS(launch_gemm(EPI_RES_F32, h->hid, b.lin2_w, p, sms, st));
+      mark(h, PC_GEMM_LIN2, st);
     }
   }
   // neck: 1x1 conv -> LayerNorm2d -> 3x3 conv -> LayerNorm2d, NCHW out
@@ -516,6 +551,7 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
     p.a_conv3 = 1; p.conv_c = 256;
     p.out = out_f32; p.ln_w = h->neck3_w; p.ln_b = h->neck3_b; p.ln_eps = 1e-6f; p.hw = 4096;
     CKS(launch_gemm(EPI_LN_NCHW, h->q, h->neck2_w, p, sms, st));
+    mark(h, PC_NECK, st, 3);
   }
   return ULLSAM_OK;
 }
@@ -533,9 +569,13 @@ int t2i_block(ullsam_handle* h, int R, int Nt, const float* q_w, const float* q_
               const float* n_w, const float* n_b, int ldkv, cudaStream_t st) {
   const int M = R * Nt;
   CKS(launch_tok_linear(lin(h->queries, h->tokens, q_w, q_b, nullptr, h->q128, M, 128, 256), st));
+  mark(h, PC_DEC_TOKENS, st, 1);
   CKS(launch_t2i_attention(h->q128, h->proj, ldkv, R, Nt, h->S, h->o128, st));
+  mark(h, PC_DEC_ATTN, st, 2);
   CKS(launch_tok_linear(lin(h->o128, nullptr, o_w, o_b, h->queries, h->tmp, M, 256, 128), st));
+  mark(h, PC_DEC_TOKENS, st, 1);
   CKS(launch_tok_ln(h->tmp, n_w, n_b, M, 1e-5f, h->queries, st));
+  mark(h, PC_DEC_TOKENS, st, 1);
   return ULLSAM_OK;
 }
 
@@ -551,44 +591,60 @@ int transformer_run(ullsam_handle* h, int R, int Nt, cudaStream_t st) {
     GemmParams p = gp(4096, fin ? 256 : 384, 256);
     p.out = h->peproj[i];
     CKS(launch_gemm(EPI_F32, h->pe_bf, fin ? h->fin_catpe_w : h->layers[i].catpe_w, p, sms, st));
+    mark(h, PC_DEC_GEMM, st, 1);
   }
   for (int i = 0; i < c.dec_depth; ++i) {
     const DecLayer& L = h->layers[i];
     const float* pe = (i == 0) ? nullptr : h->tokens;  // skip_first_layer_pe (transformer.py:157-158)
     // ---- self attention ----
     CKS(launch_tok_linear(lin(h->queries, pe, L.self.q_w, L.self.q_b, nullptr, h->tq, M, 256, 256), st));
+    mark(h, PC_DEC_TOKENS, st, 1);
     CKS(launch_tok_linear(lin(h->queries, pe, L.self.k_w, L.self.k_b, nullptr, h->tk, M, 256, 256), st));
+    mark(h, PC_DEC_TOKENS, st, 1);
     CKS(launch_tok_linear(lin(h->queries, nullptr, L.self.v_w, L.self.v_b, nullptr, h->tv, M, 256, 256), st));
+    mark(h, PC_DEC_TOKENS, st, 1);
     CKS(launch_tok_self_attn(h->tq, h->tk, h->tv, R, Nt, h->ta, st));
+    mark(h, PC_DEC_TOKENS, st, 1);
     CKS(launch_tok_linear(lin(h->ta, nullptr, L.self.o_w, L.self.o_b, (i == 0) ? nullptr : h->queries, h->tmp, M, 256, 256), st));
+    mark(h, PC_DEC_TOKENS, st, 1);
     CKS(launch_tok_ln(h->tmp, L.n1_w, L.n1_b, M, 1e-5f, h->queries, st));
+    mark(h, PC_DEC_TOKENS, st, 1);
     // ---- image-side projections for this layer: [K_t2i | V_t2i | Q_i2t] in one GEMM ----
     {
       GemmParams p = gp(rk, 384, 256);
       p.bias = L.cat_b; p.out = h->proj; p.pos = h->peproj[i]; p.pos_rows = 4096;
       CKS(launch_gemm(EPI_BF16, h->keys_bf, L.cat_w, p, sms, st));
+      mark(h, PC_DEC_GEMM, st, 1);
     }
     // ---- tokens attend to the image ----
     if (int rc = t2i_block(h, R, Nt, L.t2i_q_w, L.t2i_q_b, L.t2i_o_w, L.t2i_o_b, L.n2_w, L.n2_b, 384, st)) return rc;
     // ---- MLP ----
     CKS(launch_tok_linear(lin(h->queries, nullptr, L.mlp1_w, L.mlp1_b, nullptr, h->thid, M, c.dec_mlp_dim, 256, 2), st));
+    mark(h, PC_DEC_TOKENS, st, 1);
     CKS(launch_tok_linear(lin(h->thid, nullptr, L.mlp2_w, L.mlp2_b, h->queries, h->tmp, M, 256, c.dec_mlp_dim), st));
+    mark(h, PC_DEC_TOKENS, st, 1);
     CKS(launch_tok_ln(h->tmp, L.n3_w, L.n3_b, M, 1e-5f, h->queries, st));
+    mark(h, PC_DEC_TOKENS, st, 1);
     // ---- image attends to the tokens; keys = norm4(keys + out_proj(attn)) ----
     CKS(launch_tok_linear(lin(h->queries, h->tokens, L.i2t_k_w, L.i2t_k_b, nullptr, h->k128, M, 128, 256), st));
+    mark(h, PC_DEC_TOKENS, st, 1);
     CKS(launch_tok_linear(lin(h->queries, nullptr, L.i2t_v_w, L.i2t_v_b, nullptr, h->v128, M, 128, 256), st));
+    mark(h, PC_DEC_TOKENS, st, 1);
     CKS(launch_i2t_attention(h->proj, 384, 256, h->k128, h->v128, R, Nt, h->ao128, st));
+    mark(h, PC_DEC_ATTN, st, 1);
     {
       GemmParams p = gp(rk, 256, 128);
       p.bias = L.i2t_o_b; p.residual = h->keys; p.out = h->keys; p.out2 = h->keys_bf;
       p.ln_w = L.n4_w; p.ln_b = L.n4_b; p.ln_eps = 1e-5f;
       CKS(launch_gemm(EPI_LN_RES, h->ao128, L.i2t_o_w, p, sms, st));
+      mark(h, PC_DEC_GEMM, st, 1);
     }
   }
   {  // final token -> image attention
     GemmParams p = gp(rk, 256, 256);
     p.bias = h->fin_cat_b; p.out = h->proj; p.pos = h->peproj[c.dec_depth]; p.pos_rows = 4096;
     CKS(launch_gemm(EPI_BF16, h->keys_bf, h->fin_cat_w, p, sms, st));
+    mark(h, PC_DEC_GEMM, st, 1);
     if (int rc = t2i_block(h, R, Nt, h->fin_q_w, h->fin_q_b, h->fin_o_w, h->fin_o_b, h->nf_w, h->nf_b, 256, st)) return rc;
   }
   return ULLSAM_OK;
@@ -607,20 +663,26 @@ int decoder_run(ullsam_handle* h, const float* emb, int n_img, const float* imag
   if (nm != 4) return fail(h, ULLSAM_ERR_INVALID, "decoder: num_mask_tokens must be 4");
   if (int rc = ensure_decoder_ws(h, R, Nt)) return rc;
   CKS(launch_tok_init(h->iou_token, h->mask_tokens, nm, sparse, Ns, R, h->tokens, st));
+  mark(h, PC_DEC_TOKENS, st, 1);
   CKS(launch_keys_init(emb, R, P, dense, dense_mode, dense_batch, h->keys, h->keys_bf, st));
+  mark(h, PC_DEC_TOKENS, st, 1);
   CKS(launch_keys_init(image_pe, 1, 1, nullptr, 0, 1, nullptr, h->pe_bf, st));
+  mark(h, PC_DEC_TOKENS, st, 1);
   if (int rc = transformer_run(h, R, Nt, st)) return rc;
   // hypernetwork MLPs on the 4 mask tokens (grouped) and the IoU head on token 0
   {
     TokLinear a = lin(h->queries + 256, nullptr, h->hyp_w0, h->hyp_b0, nullptr, h->hyp1, R, 256, 256, 2);
     a.G = nm; a.ldx = Nt * 256; a.x_gs = 256; a.w_gs = 256 * 256; a.b_gs = 256; a.y_gs = static_cast<size_t>(R) * 256;
     CKS(launch_tok_linear(a, st));
+    mark(h, PC_DEC_TOKENS, st, 1);
     TokLinear b2 = lin(h->hyp1, nullptr, h->hyp_w1, h->hyp_b1, nullptr, h->hyp2, R, 256, 256, 2);
     b2.G = nm; b2.x_gs = static_cast<size_t>(R) * 256; b2.w_gs = 256 * 256; b2.b_gs = 256; b2.y_gs = static_cast<size_t>(R) * 256;
     CKS(launch_tok_linear(b2, st));
+    mark(h, PC_DEC_TOKENS, st, 1);
     TokLinear c3 = lin(h->hyp2, nullptr, h->hyp_w2, h->hyp_b2, nullptr, h->hyper, R, 32, 256, 0);
     c3.G = nm; c3.x_gs = static_cast<size_t>(R) * 256; c3.w_gs = 32 * 256; c3.b_gs = 32; c3.ldy = nm * 32; c3.y_gs = 32;
     CKS(launch_tok_linear(c3, st));
+    mark(h, PC_DEC_TOKENS, st, 1);
   }
   {
     const float* x = h->queries;
@@ -633,20 +695,24 @@ int decoder_run(ullsam_handle* h, const float* emb, int n_img, const float* imag
       TokLinear a = lin(x, nullptr, h->iou_w[i], h->iou_b[i], nullptr, y, R, N, K, last ? 0 : 2);
       a.ldx = ldx;
       CKS(launch_tok_linear(a, st));
+      mark(h, PC_DEC_TOKENS, st, 1);
       x = y;
       ldx = N;
     }
     CKS(launch_slice_copy(h->iou4, R, nm, m0, cnt, 1, iou, st));
+    mark(h, PC_DEC_TOKENS, st, 1);
   }
   {  // output_upscaling stage 1: ConvT + LayerNorm2d + GELU
     GemmParams p = gp(R * 4096, 256, 256);
     p.bias = h->up1_b; p.out = h->up_h; p.ln_w = h->upln_w; p.ln_b = h->upln_b; p.ln_eps = 1e-6f;
     CKS(launch_gemm(EPI_UP1, h->keys_bf, h->up1_w, p, sms, st));
+    mark(h, PC_DEC_UPSCALE, st, 1);
   }
   {  // stage 2: ConvT + GELU, contracted with hyper_in -> mask logits
     GemmParams p = gp(R * 16384, 128, 64);
     p.bias = h->up2_b; p.out = masks; p.hyper = h->hyper; p.mask_m0 = m0; p.mask_cnt = cnt;
     CKS(launch_gemm(EPI_MASK, h->up_h, h->up2_w, p, sms, st));
+    mark(h, PC_DEC_UPSCALE, st, 1);
   }
   return ULLSAM_OK;
 }
@@ -695,6 +761,7 @@ void ullsam_destroy(ullsam_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->staging) cudaFree(h->staging);
   if (h->staging_raw) cudaFree(h->staging_raw);
   delete h;
@@ -818,10 +885,40 @@ int ullsam_transformer_forward(ullsam_handle* h, const void* image_embedding, in
   if (int rc = ensure_decoder_ws(h, R, Nt)) return rc;
   CKC(cudaMemcpyAsync(h->tokens, point_embedding, static_cast<size_t>(R) * Nt * 256 * 4, cudaMemcpyDeviceToDevice, st));
   CKS(launch_keys_init(static_cast<const float*>(image_embedding), R, 1, nullptr, 0, 1, h->keys, h->keys_bf, st));
+  mark(h, PC_DEC_TOKENS, st, 1);
   CKS(launch_keys_init(static_cast<const float*>(image_pe), 1, 1, nullptr, 0, 1, nullptr, h->pe_bf, st));
+  mark(h, PC_DEC_TOKENS, st, 1);
   if (int rc = transformer_run(h, R, Nt, st)) return rc;
   CKC(cudaMemcpyAsync(queries, h->queries, static_cast<size_t>(R) * Nt * 256 * 4, cudaMemcpyDeviceToDevice, st));
   CKC(cudaMemcpyAsync(keys, h->keys, static_cast<size_t>(R) * 4096 * 256 * 4, cudaMemcpyDeviceToDevice, st));
+  return ULLSAM_OK;
+}
+
+unsigned long long ullsam_launch_count(const ullsam_handle* h) { return h ? h->launches : 0; }
+
+int ullsam_profile_begin(ullsam_handle* h) {
+  if (!h) return ULLSAM_ERR_INVALID;
+  h->prof_on = true;
+  h->prof_n = 0;
+  h->prof_cat.clear();
+  return ULLSAM_OK;
+}
+
+int ullsam_profile_categories(void) { return PC_COUNT; }
+const char* ullsam_profile_category_name(int i) { return (i >= 0 && i < PC_COUNT) ? kProfNames[i] : ""; }
+
+int ullsam_profile_end(ullsam_handle* h, float* ms_per_category, int* launches_per_category, int n) {
+  if (!h || !ms_per_category || !launches_per_category || n < PC_COUNT) return fail(h, ULLSAM_ERR_INVALID, "profile_end: bad argument");
+  h->prof_on = false;
+  for (int i = 0; i < n; ++i) { ms_per_category[i] = 0.f; launches_per_category[i] = 0; }
+  if (h->prof_n == 0) return ULLSAM_OK;
+  CKC(cudaEventSynchronize(h->prof_ev[h->prof_n - 1]));
+  for (size_t i = 1; i < h->prof_n; ++i) {
+    float ms = 0.f;
+    CKC(cudaEventElapsedTime(&ms, h->prof_ev[i - 1], h->prof_ev[i]));
+    ms_per_category[h->prof_cat[i]] += ms;
+    launches_per_category[h->prof_cat[i]] += 1;
+  }
   return ULLSAM_OK;
 }
 

@@ -110,6 +110,21 @@ class Engine:
     def missing(self, which: int) -> int:
         return self.lib.ullsam_missing_weights(self._h, which)
 
+    # ------------------------------------------------------------------ instrumentation
+    def launch_count(self) -> int:
+        return int(self.lib.ullsam_launch_count(self._h))
+
+    def profile_begin(self) -> None:
+        check(self.lib.ullsam_profile_begin(self._h), self._h, "ullsam_profile_begin")
+
+    def profile_end(self) -> Dict[str, Tuple[float, int]]:
+        """{category: (milliseconds, marked launches)} accumulated since ``profile_begin``."""
+        n = self.lib.ullsam_profile_categories()
+        ms = (C.c_float * n)()
+        cnt = (C.c_int * n)()
+        check(self.lib.ullsam_profile_end(self._h, ms, cnt, n), self._h, "ullsam_profile_end")
+        return {self.lib.ullsam_profile_category_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
     # ------------------------------------------------------------------ forward passes
     def encoder_forward(self, images: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
         """ImageEncoderViT.forward: [B,3,1024,1024] (fp32 / bf16) -> [B,256,64,64]."""

@@ -1,4 +1,4 @@
-"""Seeded synthetic weights and inputs for the SAM path — TEST INFRASTRUCTURE (see oracle/sam_oracle.py).
+"""Seeded synthetic weights and inputs for the SAM path (there is no network for checkpoints or datasets).
 
 Weights: a ``state_dict`` with exactly the reference's key names and shapes, drawn from a
 seeded CPU generator: Linear/Conv weights and biases ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in)) (the magnitude of
@@ -17,7 +17,7 @@ from typing import Dict, Tuple
 
 import torch
 
-from .sam_oracle import SamConfig
+from .config import SamConfig
 
 
 def _uniform(gen, shape, bound):
@@ -163,3 +163,17 @@ def make_llm_map(P: int, seed: int = 11, C: int = 256, g: int = 64) -> torch.Ten
     """Stand-in for InternVLSAMModel.text_aware_dense_feature's [P,256,64,64] map (modeling_internvl_sam.py:253-270)."""
     gen = torch.Generator().manual_seed(seed)
     return torch.randn(P, C, g, g, generator=gen)
+
+
+def make_prompt_embeddings(B: int, Ns: int = 2, seed: int = 13, C: int = 256, g: int = 64):
+    """Synthetic stand-ins for PromptEncoder's outputs (the path's inputs; the module itself stays in PyTorch):
+    sparse [B,Ns,C], image_pe [1,C,g,g] (a random-Fourier positional encoding) and the no-mask dense vector [C]."""
+    gen = torch.Generator().manual_seed(seed)
+    sparse = torch.randn(B, Ns, C, generator=gen)
+    gauss = torch.randn(2, C // 2, generator=gen)
+    ys = (torch.arange(g, dtype=torch.float32) + 0.5) / g
+    coords = torch.stack([ys[None, :].expand(g, g), ys[:, None].expand(g, g)], dim=-1)
+    proj = 2.0 * math.pi * ((2.0 * coords - 1.0) @ gauss)
+    pe = torch.cat([torch.sin(proj), torch.cos(proj)], dim=-1).permute(2, 0, 1)[None].contiguous()
+    dense_vec = torch.randn(C, generator=gen)
+    return sparse, pe, dense_vec
