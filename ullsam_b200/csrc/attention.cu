@@ -6,21 +6,23 @@
 // for the global 64x64 grid (T = 4096 keys) and for 14x14 windows (T = 196 keys, all of them real keys:
 // the zero-padded rows of edge windows carry k = v = qkv.bias and are attended to, :168-172, 243-264).
 //
-// One CTA = 256 query rows (two 128-row tiles) of one (group, head):
-//   warps 0-3 / 4-7 : softmax warpgroup for query tile 0 / 1 (thread == query row == TMEM lane)
-//   warp 8          : TMA producer (Q once; K/V tiles through an mbarrier ring; the rel-pos tables)
-//   warp 9          : tcgen05.mma issuer (single thread) + TMEM allocator
-// Flash-style loop over key tiles of RPT grid rows (global: 2 x 64 = 128 keys; windowed: 8 x 14 = 112):
-//   S = Q K^T        (SS MMA, fp32 in TMEM)            -> softmax warpgroup adds the bias, exponentiates,
-//   P (bf16, smem, 128B-swizzled K-major)                 writes P and signals the MMA warp
-//   O += P V         (SS MMA, V is the MN-major operand, O accumulates in TMEM)
-// The two query tiles ping-pong on the tensor core, so one tile's softmax overlaps the other's MMAs.
-// The running max is only refreshed when it grows by more than 2^8 (exact: softmax is invariant to the
-// reference point; O and the row sum are rescaled together), so the O round-trip through registers is rare.
+// CTA = QT query tiles of 128 rows of one (group, head):
+//   global   (GRID 64): QT = 2, 384 threads, one CTA per SM, 32 key tiles of 128 keys (2 grid rows)
+//   windowed (GRID 14): QT = 1, 192 threads, two CTAs per SM, 2 key tiles of 112 keys (8 grid rows)
+// Warp roles: QT softmax warpgroups (thread == query row == TMEM lane), one TMA producer warp, one
+// tcgen05.mma issuer warp (single thread) that also owns the TMEM allocation.
+//
+// Flash-style loop.  S = Q K^T lands in a ring of TMEM slots (3 for global, 2 for windowed) so the tensor
+// core runs ahead of the softmax; the softmax warpgroup adds the bias, exponentiates in ONE pass against a
+// stale running maximum, writes P (bf16, 128B-swizzled K-major) to shared memory and signals the MMA warp,
+// which accumulates O += P V in TMEM (V is the MN-major operand).  The running maximum is refreshed lazily:
+// when a tile's maximum exceeds the reference by more than 2^8 the row's O and sum are rescaled before the
+// next tile (exact: softmax is invariant to the reference point), and a tile whose exponent would leave the
+// fp32-safe range is simply redone with the refreshed reference.
 //
 // Bias: the prologue computes Tw = Q rel_pos_w^T and Th = Q rel_pos_h^T with two extra MMAs per query tile
-// (tables zero-padded to NREL rows), each thread gathers its own 2*GRID values through a shared-memory
-// scatter, keeps rel_w in registers and (global) parks rel_h as packed half2 in spare TMEM columns.
+// (tables zero-padded to NREL rows); each thread gathers its own 2*GRID values through a shared-memory
+// scatter, keeps rel_w (and, windowed, rel_h) in registers and (global) parks rel_h as half2 in shared memory.
 #include "attention.h"
 
 #include "common.cuh"
@@ -30,29 +32,37 @@ namespace ullsam {
 
 namespace {
 
-constexpr int ATT_THREADS = 384;  // 2 softmax warpgroups + 1 control warpgroup (TMA, MMA, 2 idle warps)
 constexpr float kLog2e = 1.4426950408889634f;
 
 template <int GRID>
 struct AttCfg {
+  static constexpr bool GLOBAL = (GRID == 64);
+  static constexpr int QT = GLOBAL ? 2 : 1;               // query tiles per CTA
+  static constexpr int THREADS = GLOBAL ? 384 : 192;
+  static constexpr int CTRL_WARP0 = QT * 4;               // first control warp (TMA); +1 = MMA
   static constexpr int T = GRID * GRID;
-  static constexpr int RPT = (GRID == 64) ? 2 : 8;        // key-grid rows per tile
+  static constexpr int RPT = GLOBAL ? 2 : 8;              // key-grid rows per tile
   static constexpr int BN = RPT * GRID;                   // keys per tile: 128 / 112
   static constexpr int NT = (T + BN - 1) / BN;            // 32 / 2
-  static constexpr int NREL = (GRID == 64) ? 128 : 32;    // padded rows of the rel-pos tables
-  static constexpr int STAGES = 3;
+  static constexpr int NITEMS = NT * QT;                  // (tile, q-tile) work items in issue order
+  static constexpr int NSLOT = GLOBAL ? 3 : 2;            // S ring in TMEM
+  static constexpr int NREL = GLOBAL ? 128 : 32;          // padded rows of the rel-pos tables
+  static constexpr int STAGES = GLOBAL ? 3 : 2;
   static constexpr int QBYTES = 128 * 128;                // one 128 x 64 bf16 tile
-  static constexpr int KVBYTES = 128 * 128;               // stage slot for K (and for V), BN <= 128 rows
-  static constexpr int OFF_Q = 0;                         // 2 tiles
-  static constexpr int OFF_KV = 2 * QBYTES;               // STAGES x (K slot, V slot)
-  static constexpr int OFF_P = OFF_KV + STAGES * 2 * KVBYTES;  // 2 q-tiles x 2 k-blocks x 16 KB
-  static constexpr int OFF_BAR = OFF_P + 4 * 16384;
-  static constexpr int NBAR = 3 + 2 * STAGES + 6;
+  static constexpr int KVSLOT = BN * 128;                 // one K (or V) tile: 16 KB / 14 KB
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_KV = QT * QBYTES;              // STAGES x (K slot, V slot)
+  static constexpr int OFF_P = OFF_KV + STAGES * 2 * KVSLOT;   // QT x 2 k-blocks x 16 KB
+  static constexpr int OFF_RELH = OFF_P + QT * 32768;     // global: half2 rel_h [32][256]
+  static constexpr int OFF_BAR = OFF_RELH + (GLOBAL ? 32 * 256 * 4 : 0);
+  static constexpr int NBAR = 3 + 2 * STAGES + NSLOT + 2 * QT;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
-  // TMEM columns
-  static constexpr int COL_S = 0;       // + qt*128
-  static constexpr int COL_O = 256;     // + qt*64
-  static constexpr int COL_RELH = 384;  // + qt*32 (global only: packed half2 rel_h, column j = rows 2j, 2j+1)
+  static constexpr int TMEM_COLS = GLOBAL ? 512 : 256;
+  // TMEM columns.  global: S slots 0/128/256, O 384 + qt*64.  windowed: S slots 0/128, O aliases slot 0.
+  static constexpr int COL_O = GLOBAL ? 384 : 0;
+  // where the rel-pos tables ride until the prologue MMAs retire
+  static constexpr int OFF_RELTAB_W = GLOBAL ? OFF_KV + (STAGES - 1) * 2 * KVSLOT : OFF_P + 16384;
+  static constexpr int OFF_RELTAB_H = GLOBAL ? OFF_RELTAB_W + KVSLOT : OFF_RELTAB_W + 4096;
 };
 
 ULLSAM_DEVICE float ex2(float x) {
@@ -61,19 +71,13 @@ ULLSAM_DEVICE float ex2(float x) {
   return y;
 }
 
-ULLSAM_DEVICE void tmem_ld1(uint32_t taddr, uint32_t& v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
-}
-
 template <int GRID>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(AttCfg<GRID>::THREADS, AttCfg<GRID>::GLOBAL ? 1 : 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmRh,
                  const __grid_constant__ CUtensorMap tmRw, int heads, __nv_bfloat16* __restrict__ out) {
   using A = AttCfg<GRID>;
-  constexpr int S = A::STAGES;
-  constexpr int BN = A::BN;
-  constexpr int NT = A::NT;
+  constexpr int S = A::STAGES, BN = A::BN, NT = A::NT, QT = A::QT, NSLOT = A::NSLOT, NITEMS = A::NITEMS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A::OFF_BAR);
@@ -82,34 +86,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* pro_consumed = bars + 2;
   uint64_t* kv_full = bars + 3;
   uint64_t* kv_empty = kv_full + S;
-  uint64_t* s_full = kv_empty + S;   // [2]
-  uint64_t* p_ready = s_full + 2;    // [2]
-  uint64_t* o_done = p_ready + 2;    // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_full = kv_empty + S;      // [NSLOT]
+  uint64_t* p_ready = s_full + NSLOT;   // [QT]
+  uint64_t* o_done = p_ready + QT;      // [QT]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + QT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gh = blockIdx.y;                       // group * heads + head
-  const int qblock = blockIdx.x;                   // 256-row block of queries inside the group
+  const int qblock = blockIdx.x;                   // block of QT*128 queries inside the group
   const int row_base = gh * A::T;                  // first row of this (group, head) in q/k/v
-  const int q_row0 = row_base + qblock * 256;
+  const int q_row0 = row_base + qblock * (QT * 128);
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     mbar_init(pro_mma_done, 1);
-    mbar_init(pro_consumed, 8);
+    mbar_init(pro_consumed, QT * 4);
     for (int i = 0; i < S; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
+    for (int i = 0; i < NSLOT; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < QT; ++i) {
       mbar_init(&p_ready[i], 4);
       mbar_init(&o_done[i], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 9) {
-    tmem_alloc(tmem_ptr_smem, 512);
+  if (warp == A::CTRL_WARP0 + 1) {
+    tmem_alloc(tmem_ptr_smem, A::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -117,35 +121,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp >= 8) {
-    // (register rebalancing via setmaxnreg measured worse with ptxas 12.9 here)
-  } else {
-    ;
-  }
-
-  if (warp == 8) {
+  if (warp == A::CTRL_WARP0) {
     // =========================================== TMA producer ===========================================
     if (lane == 0) {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
       uint8_t* kv = smem + A::OFF_KV;
-      // Q tiles + rel-pos tables (tables ride in the LAST ring stage until the prologue MMAs retire)
-      mbar_arrive_expect_tx(q_full, 2 * A::QBYTES + 2 * A::NREL * 128);
-      tma_load_2d(smem + A::OFF_Q, &tmQ, q_full, 0, q_row0);
-      tma_load_2d(smem + A::OFF_Q + A::QBYTES, &tmQ, q_full, 0, q_row0 + 128);
-      tma_load_2d(kv + (S - 1) * 2 * A::KVBYTES, &tmRw, q_full, 0, 0);
-      tma_load_2d(kv + (S - 1) * 2 * A::KVBYTES + A::KVBYTES, &tmRh, q_full, 0, 0);
+      mbar_arrive_expect_tx(q_full, QT * A::QBYTES + 2 * A::NREL * 128);
+#pragma unroll
+      for (int qt = 0; qt < QT; ++qt) tma_load_2d(smem + A::OFF_Q + qt * A::QBYTES, &tmQ, q_full, 0, q_row0 + qt * 128);
+      tma_load_2d(smem + A::OFF_RELTAB_W, &tmRw, q_full, 0, 0);
+      tma_load_2d(smem + A::OFF_RELTAB_H, &tmRh, q_full, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < NT; ++j) {
-        if (j == S - 1) mbar_wait(pro_mma_done, 0);
+        if (A::GLOBAL && j == S - 1) mbar_wait(pro_mma_done, 0);  // that stage still holds the rel-pos tables
         mbar_wait(&kv_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&kv_full[stage], 2 * BN * 128);
-        tma_load_2d(kv + stage * 2 * A::KVBYTES, &tmK, &kv_full[stage], 0, row_base + j * BN);
-        tma_load_2d(kv + stage * 2 * A::KVBYTES + A::KVBYTES, &tmV, &kv_full[stage], 0, row_base + j * BN);
+        mbar_arrive_expect_tx(&kv_full[stage], 2 * A::KVSLOT);
+        tma_load_2d(kv + stage * 2 * A::KVSLOT, &tmK, &kv_full[stage], 0, row_base + j * BN);
+        tma_load_2d(kv + stage * 2 * A::KVSLOT + A::KVSLOT, &tmV, &kv_full[stage], 0, row_base + j * BN);
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == A::CTRL_WARP0 + 1) {
     // =========================================== MMA issuer =============================================
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, BN, 0, 0);
@@ -155,37 +152,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t skv = smem_u32(smem + A::OFF_KV);
       const uint32_t sp = smem_u32(smem + A::OFF_P);
 
-      // ---- prologue: Tw[qt] = Q[qt] Rw^T, Th[qt] = Q[qt] Rh^T ----
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      {
-        const uint64_t drw = make_smem_desc_sw128(skv + (S - 1) * 2 * A::KVBYTES, 16, 1024);
-        const uint64_t drh = make_smem_desc_sw128(skv + (S - 1) * 2 * A::KVBYTES + A::KVBYTES, 16, 1024);
-#pragma unroll
-        for (int qt = 0; qt < 2; ++qt) {
-          const uint64_t dq = make_smem_desc_sw128(sq + qt * A::QBYTES, 16, 1024);
-          const uint32_t col_w = (GRID == 64) ? qt * 128 : qt * 64;
-          const uint32_t col_h = (GRID == 64) ? 256 + qt * 128 : qt * 64 + 32;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + col_w, dq + 2 * k, drw + 2 * k, idesc_rel, k != 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + col_h, dq + 2 * k, drh + 2 * k, idesc_rel, k != 0);
+      auto issue_qk = [&](int n) {  // S[slot n % NSLOT] = Q[qt] K(j)^T
+        const int j = n / QT, qt = n % QT, stage = j % S;
+        if (qt == 0) {
+          mbar_wait(&kv_full[stage], (j / S) & 1);
+          tc_fence_after();
         }
-      }
-      umma_commit(pro_mma_done);
-      mbar_wait(pro_consumed, 0);
-      tc_fence_after();
-
-      auto issue_qk = [&](int qt, int stage) {
         const uint64_t dq = make_smem_desc_sw128(sq + qt * A::QBYTES, 16, 1024);
-        const uint64_t dk = make_smem_desc_sw128(skv + stage * 2 * A::KVBYTES, 16, 1024);
+        const uint64_t dk = make_smem_desc_sw128(skv + stage * 2 * A::KVSLOT, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem_base + A::COL_S + qt * 128, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
-        umma_commit(&s_full[qt]);
+        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + (n % NSLOT) * 128, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[n % NSLOT]);
       };
-      auto issue_pv = [&](int qt, int stage, int j) {
-        const uint64_t dv = make_smem_desc_sw128(skv + stage * 2 * A::KVBYTES + A::KVBYTES, 16, 1024);
+      auto issue_pv = [&](int n) {  // O[qt] (+)= P[qt] V(j)
+        const int j = n / QT, qt = n % QT, stage = j % S;
+        const uint64_t dv = make_smem_desc_sw128(skv + stage * 2 * A::KVSLOT + A::KVSLOT, 16, 1024);
 #pragma unroll
         for (int s = 0; s < BN / 16; ++s) {
           const uint64_t dp = make_smem_desc_sw128(sp + qt * 32768 + (s >> 2) * 16384, 16, 1024) + 2 * (s & 3);
@@ -193,57 +174,61 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           umma_ss(tmem_base + A::COL_O + qt * 64, dp, dv + s * 128, idesc_pv, (j | s) != 0);
         }
         umma_commit(&o_done[qt]);
+        if (qt == QT - 1) umma_commit(&kv_empty[stage]);
       };
 
-      int stage = 0;
-      uint32_t phase = 0;
-      mbar_wait(&kv_full[0], 0);
+      // ---- prologue: Tw[qt] = Q[qt] Rw^T, Th[qt] = Q[qt] Rh^T ----
+      mbar_wait(q_full, 0);
       tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      for (int j = 0; j < NT; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == S) { nstage = 0; nphase ^= 1; }
+      {
+        const uint64_t drw = make_smem_desc_sw128(smem_u32(smem + A::OFF_RELTAB_W), 16, 1024);
+        const uint64_t drh = make_smem_desc_sw128(smem_u32(smem + A::OFF_RELTAB_H), 16, 1024);
 #pragma unroll
-        for (int qt = 0; qt < 2; ++qt) {
-          mbar_wait(&p_ready[qt], j & 1);
-          tc_fence_after();
-          issue_pv(qt, stage, j);
-          if (j + 1 < NT) {
-            if (qt == 0) {
-              mbar_wait(&kv_full[nstage], nphase);
-              tc_fence_after();
-            }
-            issue_qk(qt, nstage);
-          }
+        for (int qt = 0; qt < QT; ++qt) {
+          const uint64_t dq = make_smem_desc_sw128(sq + qt * A::QBYTES, 16, 1024);
+          const uint32_t col_w = A::GLOBAL ? qt * 128 : 128;
+          const uint32_t col_h = A::GLOBAL ? 256 + qt * 128 : 160;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + col_w, dq + 2 * k, drw + 2 * k, idesc_rel, k != 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + col_h, dq + 2 * k, drh + 2 * k, idesc_rel, k != 0);
         }
-        umma_commit(&kv_empty[stage]);
-        stage = nstage;
-        phase = nphase;
+      }
+      umma_commit(pro_mma_done);
+      if (!A::GLOBAL) issue_qk(0);  // windowed: slot 0 does not overlap the prologue tables (slot 1)
+      mbar_wait(pro_consumed, 0);
+      tc_fence_after();
+      for (int n = A::GLOBAL ? 0 : 1; n < NSLOT && n < NITEMS; ++n) issue_qk(n);
+      for (int n = 0; n < NITEMS; ++n) {
+        mbar_wait(&p_ready[n % QT], (n / QT) & 1);  // P(n) written, S(n) fully consumed -> its slot is free
+        tc_fence_after();
+        if (n + NSLOT < NITEMS) issue_qk(n + NSLOT);
+        issue_pv(n);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < A::CTRL_WARP0) {
     // =========================================== softmax warpgroups =====================================
     const int qt = warp >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;           // row inside the query tile == TMEM lane
-    const int tid256 = qt * 128 + r;          // row inside the CTA
+    const int tidq = qt * 128 + r;            // row inside the CTA
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const int tq = qblock * 256 + tid256;     // query index inside the group
+    const int tq = qblock * (QT * 128) + tidq;  // query index inside the group
     const int qh = tq / GRID, qw = tq % GRID;
-    float* scratch = reinterpret_cast<float*>(smem + A::OFF_P);  // [NRELV][256] fp32, free until the first P
+    constexpr int NROWS = QT * 128;
+    float* scratch = reinterpret_cast<float*>(smem + A::OFF_P);  // [<=64][NROWS] fp32, free until the first P
+    uint32_t* relh_s = reinterpret_cast<uint32_t*>(smem + A::OFF_RELH);
 
-    constexpr int NW = (GRID == 64) ? 64 : 14;
+    constexpr int NW = A::GLOBAL ? 64 : 14;
     float relw[NW];
-    float relh_reg[(GRID == 64) ? 1 : 14];
+    float relh_reg[A::GLOBAL ? 1 : 14];
 
     // ------------------------------------ prologue: gather the bias rows ------------------------------
     mbar_wait(pro_mma_done, 0);
     tc_fence_after();
     {
-      const uint32_t col_w = (GRID == 64) ? qt * 128 : qt * 64;
-      const uint32_t col_h = (GRID == 64) ? 256 + qt * 128 : qt * 64 + 32;
+      const uint32_t col_w = A::GLOBAL ? qt * 128 : 128;
+      const uint32_t col_h = A::GLOBAL ? 256 + qt * 128 : 160;
       // rel_w: Tw[row][i], i = qw - kw + GRID-1  ->  scratch[kw][row]
 #pragma unroll
       for (int c = 0; c < A::NREL / 32; ++c) {
@@ -253,11 +238,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int kw = qw + (GRID - 1) - (c * 32 + i);
-          if (kw >= 0 && kw < GRID) scratch[kw * 256 + tid256] = __uint_as_float(v[i]) * kLog2e;
+          if (kw >= 0 && kw < GRID) scratch[kw * NROWS + tidq] = __uint_as_float(v[i]) * kLog2e;
         }
       }
 #pragma unroll
-      for (int kw = 0; kw < NW; ++kw) relw[kw] = scratch[kw * 256 + tid256];
+      for (int kw = 0; kw < NW; ++kw) relw[kw] = scratch[kw * NROWS + tidq];
       // rel_h: Th[row][i], i = qh - kh + GRID-1  ->  scratch[kh][row]   (same thread re-uses its own column)
 #pragma unroll
       for (int c = 0; c < A::NREL / 32; ++c) {
@@ -267,140 +252,133 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int kh = qh + (GRID - 1) - (c * 32 + i);
-          if (kh >= 0 && kh < GRID) scratch[kh * 256 + tid256] = __uint_as_float(v[i]) * kLog2e;
+          if (kh >= 0 && kh < GRID) scratch[kh * NROWS + tidq] = __uint_as_float(v[i]) * kLog2e;
         }
       }
-      if constexpr (GRID == 64) {
-        uint32_t packed[32];
+      if constexpr (A::GLOBAL) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const __half2 h = __floats2half2_rn(scratch[(2 * j) * 256 + tid256], scratch[(2 * j + 1) * 256 + tid256]);
-          packed[j] = *reinterpret_cast<const uint32_t*>(&h);
+          const __half2 h = __floats2half2_rn(scratch[(2 * j) * NROWS + tidq], scratch[(2 * j + 1) * NROWS + tidq]);
+          relh_s[j * NROWS + tidq] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        // every prologue TMEM read of both warpgroups must retire before columns 384.. are overwritten
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        tmem_st32(lane_addr + A::COL_RELH + qt * 32, packed);
-        tmem_wait_st();
         relh_reg[0] = 0.f;
       } else {
 #pragma unroll
-        for (int kh = 0; kh < 14; ++kh) relh_reg[kh] = scratch[kh * 256 + tid256];
+        for (int kh = 0; kh < 14; ++kh) relh_reg[kh] = scratch[kh * NROWS + tidq];
       }
     }
     tc_fence_before();
-    // the scratch region becomes the P buffers: make sure both warpgroups are done with it
-    asm volatile("bar.sync 3, 256;" ::: "memory");
+    // the scratch region becomes the P buffers: make sure every softmax thread is done with it
+    asm volatile("bar.sync 2, %0;" ::"n"(NROWS) : "memory");
     if (lane == 0) mbar_arrive(pro_consumed);
 
     // ------------------------------------ main loop ---------------------------------------------------
     const float cs = 0.125f * kLog2e;  // head_dim 64: scale = 1/8, folded with log2(e)
-    float m_used = -INFINITY;
+    float m_used = 0.f;                // reference point of the exponentials (log2 units)
     float l = 0.f;
+    float pend = 0.f;                  // pending shift of the reference (applied before the next tile)
     uint8_t* prow = smem + A::OFF_P + qt * 32768 + r * 128;
     const int rx = r & 7;
+    const uint32_t o_addr = lane_addr + A::COL_O + qt * 64;
+
+    // O *= 2^-shift, l *= 2^-shift, m_used += shift  (whole warp takes part: tcgen05.ld/st are collective)
+    auto shift_reference = [&](float shift, bool o_valid) {
+      const float alpha = ex2(-shift);
+      l *= alpha;
+      m_used += shift;
+      if (o_valid) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld32(o_addr + c * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(o_addr + c * 32, o);
+        }
+        tmem_wait_st();
+      }
+    };
 
 #pragma unroll 1
     for (int j = 0; j < NT; ++j) {
-      mbar_wait(&s_full[qt], j & 1);
+      const int n = j * QT + qt;
+      const uint32_t s_addr = lane_addr + (n % NSLOT) * 128;
+      mbar_wait(&s_full[n % NSLOT], (n / NSLOT) & 1);
+      if (j > 0) mbar_wait(&o_done[qt], (j - 1) & 1);  // PV(j-1) retired: O is quiescent, P may be overwritten
       tc_fence_after();
+      if (__any_sync(0xffffffffu, pend != 0.f)) shift_reference(pend, j > 0);
+      pend = 0.f;
+
       float rh0 = 0.f, rh1 = 0.f;
-      if constexpr (GRID == 64) {
-        uint32_t hp;
-        tmem_ld1(lane_addr + A::COL_RELH + qt * 32 + j, hp);
-        tmem_wait_ld();
+      float rht[8];  // windowed: rel_h of the 8 key-grid rows of this tile
+      if constexpr (A::GLOBAL) {
+        const uint32_t hp = relh_s[j * NROWS + tidq];
         const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hp));
         rh0 = f.x;
         rh1 = f.y;
-      }
-      float rht[8];  // windowed: rel_h of the 8 key-grid rows of this tile
-      if constexpr (GRID != 64) {
+        rht[0] = 0.f;
+      } else {
 #pragma unroll
         for (int a = 0; a < 8; ++a) rht[a] = (j == 0) ? relh_reg[a] : ((8 + a < 14) ? relh_reg[(8 + a) % 14] : 0.f);
-      } else {
-        rht[0] = 0.f;
       }
-      // bias of column `col` (0..BN-1) of tile j, in log2 units, excluding the running max
-      auto bias_of = [&](int col) -> float {
-        if constexpr (GRID == 64) {
-          return relw[col & 63] + ((col < 64) ? rh0 : rh1);
-        } else {
-          // keys of tile j: t = j*112 + col, kh = t / 14, kw = t % 14  (col / 14 and col % 14 are static)
-          return relw[col % 14] + rht[col / 14];
-        }
-      };
-      const int valid_cols = (GRID == 64) ? BN : ((j == NT - 1) ? (A::T - (NT - 1) * BN) : BN);
+      const int valid_cols = A::GLOBAL ? BN : ((j == NT - 1) ? (A::T - (NT - 1) * BN) : BN);
 
-      // ---- pass 1: row max of the biased scores ----
-      float mx = -INFINITY;
+      float amax, ls;
+      bool redo;
+      do {
+        amax = -INFINITY;
+        ls = 0.f;
+        const float c0 = rh0 - m_used, c1 = rh1 - m_used;
+        float rhm[8];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + A::COL_S + qt * 128 + c * 32, v);
-        tmem_wait_ld();
+        for (int a = 0; a < 8; ++a) rhm[a] = rht[a] - m_used;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = c * 32 + i;
-          if (col < BN) {
-            float t = fmaf(__uint_as_float(v[i]), cs, bias_of(col));
-            if (GRID != 64 && col >= valid_cols) t = -INFINITY;
-            mx = fmaxf(mx, t);
+        for (int c = 0; c < 4; ++c) {
+          if (c * 32 >= BN) break;
+          uint32_t v[32];
+          tmem_ld32(s_addr + c * 32, v);
+          tmem_wait_ld();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int col = c * 32 + i + u;
+              p[u] = 0.f;
+              if (col < BN) {
+                float b;
+                if constexpr (A::GLOBAL) b = relw[col & 63] + ((col < 64) ? c0 : c1);
+                else b = relw[col % 14] + rhm[col / 14];
+                const float arg = fmaf(__uint_as_float(v[i + u]), cs, b);
+                if (A::GLOBAL || col < valid_cols) {
+                  amax = fmaxf(amax, arg);
+                  p[u] = ex2(arg);
+                }
+              }
+            }
+            ls += p[0] + p[1];
+            pk[i >> 1] = pack_bf16(p[0], p[1]);
+          }
+          uint8_t* dst = prow + (c >> 1) * 16384;
+          const int cc0 = (c & 1) * 4;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (c * 32 + u * 8 < BN)
+              *reinterpret_cast<uint4*>(dst + (((cc0 + u) ^ rx) << 4)) =
+                  make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
           }
         }
-      }
-      // ---- running max, refreshed lazily ----
-      const bool need = mx > m_used + 8.0f;
-      if (j > 0) {
-        mbar_wait(&o_done[qt], (j - 1) & 1);  // PV(j-1) retired: O is quiescent and P may be overwritten
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? ex2(m_used - mx) : 1.0f;
-          l *= alpha;
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld32(lane_addr + A::COL_O + qt * 64 + c * 32, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(lane_addr + A::COL_O + qt * 64 + c * 32, o);
-          }
-          tmem_wait_st();
-        }
-      }
-      if (need) m_used = mx;
+        // exponent outside the fp32-safe range (only plausible on the first tile): refresh and redo the tile
+        const bool bad = (amax > 100.f) || (j == 0 && amax < -100.f);
+        redo = __any_sync(0xffffffffu, bad);
+        if (redo) shift_reference(bad ? amax : 0.f, j > 0);
+      } while (redo);
+      l += ls;
+      // lazy refresh of the reference: on the first tile in both directions, later only upwards
+      if (amax > 8.f || (j == 0 && amax < -8.f)) pend = amax;
 
-      // ---- pass 2: P = exp2(t - m), row sum, bf16 P to shared memory (swizzled K-major) ----
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c * 32 >= BN) break;
-        uint32_t v[32];
-        tmem_ld32(lane_addr + A::COL_S + qt * 128 + c * 32, v);
-        tmem_wait_ld();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = 0.f, p1 = 0.f;
-          const int col = c * 32 + i;
-          if (col < BN) {
-            p0 = ex2(fmaf(__uint_as_float(v[i]), cs, bias_of(col) - m_used));
-            if (GRID != 64 && col >= valid_cols) p0 = 0.f;
-          }
-          if (col + 1 < BN) {
-            p1 = ex2(fmaf(__uint_as_float(v[i + 1]), cs, bias_of(col + 1) - m_used));
-            if (GRID != 64 && col + 1 >= valid_cols) p1 = 0.f;
-          }
-          l += p0 + p1;
-          pk[i >> 1] = pack_bf16(p0, p1);
-        }
-        uint8_t* dst = prow + (c >> 1) * 16384;
-        const int cc0 = (c & 1) * 4;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (c * 32 + u * 8 < BN)
-            *reinterpret_cast<uint4*>(dst + (((cc0 + u) ^ rx) << 4)) =
-                make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-        }
-      }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -412,7 +390,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_after();
     const float inv_l = 1.0f / l;
     long out_row = -1;
-    if constexpr (GRID == 64) {
+    if constexpr (A::GLOBAL) {
       out_row = static_cast<long>(gh / heads) * A::T + tq;
     } else {
       if (tq < A::T) {
@@ -426,7 +404,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
-      tmem_ld32(lane_addr + A::COL_O + qt * 64 + c * 32, o);
+      tmem_ld32(o_addr + c * 32, o);
       tmem_wait_ld();
       if (out_row >= 0) {
         uint4* dst = reinterpret_cast<uint4*>(out + (out_row * heads + head) * 64 + c * 32);
@@ -442,9 +420,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == A::CTRL_WARP0 + 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, A::TMEM_COLS);
   }
 }
 
@@ -467,8 +445,8 @@ const char* launch_t(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     if (ce != cudaSuccess) return cudaGetErrorString(ce);
     configured = true;
   }
-  dim3 grid((A::T + 255) / 256, G * heads);
-  kern<<<grid, ATT_THREADS, A::TOTAL, stream>>>(tq, tk, tv, trh, trw, heads, out);
+  dim3 grid((A::T + A::QT * 128 - 1) / (A::QT * 128), G * heads);
+  kern<<<grid, A::THREADS, A::TOTAL, stream>>>(tq, tk, tv, trh, trw, heads, out);
   cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? nullptr : cudaGetErrorString(ce);
 }

@@ -66,16 +66,18 @@ ULLSAM_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
       : "memory");
 }
 
+// try_wait suspends the thread in hardware until the phase completes or the hint (ns) expires, so waiting
+// warps do not burn issue slots that the compute warps of the same SM sub-partition need.
 ULLSAM_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
@@ -85,7 +87,7 @@ ULLSAM_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << 22)) {
       printf("ullsam: mbarrier timeout block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x,
              blockIdx.y, threadIdx.x, smem_u32(bar), parity);
       __trap();

@@ -736,7 +736,7 @@ int ullsam_create(const ullsam_config* cfg, int device, ullsam_handle** out) {
     return fail(nullptr, ULLSAM_ERR_INVALID, "create: kernels are specialised for img 1024 / patch 16 / window 14 / out 256");
   if (cfg->embed_dim != cfg->num_heads * 64 || (cfg->embed_dim != 768 && cfg->embed_dim != 1024 && cfg->embed_dim != 1280))
     return fail(nullptr, ULLSAM_ERR_INVALID, "create: embed_dim must be 768/1024/1280 with 64-wide heads");
-  if (cfg->mlp_dim % 256 != 0 || cfg->num_global < 0 || cfg->num_global > 8)
+  if (cfg->mlp_dim % 256 != 0 || cfg->depth < 0 || cfg->num_global < 0 || cfg->num_global > 8)
     return fail(nullptr, ULLSAM_ERR_INVALID, "create: bad mlp_dim / global_attn_indexes");
   if (cfg->transformer_dim != 256 || cfg->dec_heads != 8 || cfg->num_mask_tokens != 4 || cfg->dec_mlp_dim % 4 != 0 ||
       cfg->dec_mlp_dim > 2048 || cfg->iou_head_hidden != 256 || cfg->iou_head_depth < 2 || cfg->dec_depth < 1)
@@ -746,7 +746,7 @@ int ullsam_create(const ullsam_config* cfg, int device, ullsam_handle** out) {
   h->cfg = *cfg;
   h->device = device;
   h->sms = prop.multiProcessorCount;
-  register_encoder(h);
+  if (cfg->depth > 0) register_encoder(h);  // depth == 0: decoder-only handle (MaskDecoder / TwoWayTransformer shims)
   register_decoder(h);
   if (h->alloc_failed) {
     ullsam_destroy(h);
@@ -831,6 +831,7 @@ int ullsam_encoder_forward(ullsam_handle* h, const void* images, int dtype, int 
   if (dtype != ULLSAM_F32 && dtype != ULLSAM_BF16) return fail(h, ULLSAM_ERR_INVALID, "encoder_forward: images must be f32 or bf16");
   if (out_dtype != ULLSAM_F32 && out_dtype != ULLSAM_BF16) return fail(h, ULLSAM_ERR_INVALID, "encoder_forward: output must be f32 or bf16");
   if (B < 0) return fail(h, ULLSAM_ERR_INVALID, "encoder_forward: negative batch");
+  if (h->cfg.depth <= 0) return fail(h, ULLSAM_ERR_STATE, "encoder_forward: this handle was created without an encoder (depth 0)");
   if (int rc = check_ready(h, 0)) return rc;
   CKC(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -926,6 +927,7 @@ int ullsam_segment_host(ullsam_handle* h, const float* images_host, int B, const
                         int Ns, const float* dense_vec_host, int multimask, float* masks_host, float* iou_host, float* emb_host) {
   if (!h || !images_host || !image_pe_host || !sparse_host || !dense_vec_host || !masks_host || !iou_host || B <= 0 || Ns <= 0)
     return fail(h, ULLSAM_ERR_INVALID, "segment_host: null argument");
+  if (h->cfg.depth <= 0) return fail(h, ULLSAM_ERR_STATE, "segment_host: this handle was created without an encoder (depth 0)");
   if (int rc = check_ready(h, 0)) return rc;
   if (int rc = check_ready(h, 1)) return rc;
   CKC(cudaSetDevice(h->device));
