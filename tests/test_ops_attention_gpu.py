@@ -93,3 +93,16 @@ def test_im2col_matches_unfold():
         got = ops.im2col(t)
         assert torch.equal(got, ref.to(torch.bfloat16) if t.dtype == torch.float32 else
                            t.reshape(2, 3, 64, 16, 64, 16).permute(0, 2, 4, 1, 3, 5).reshape(2 * 4096, 768))
+
+
+@pytest.mark.parametrize("grid,G,heads", [(64, 4, 12), (14, 150, 12)])
+def test_attention_is_deterministic(grid, G, heads):
+    """Race detector: the fused kernel must be bit-reproducible run to run (mbarrier / TMEM hand-offs)."""
+    from ullsam_b200 import ops
+
+    q, k, v, rel_h, rel_w = _inputs(G, heads, grid, 21, 0.25)
+    ref = ops.attention(q, k, v, rel_h, rel_w, grid)
+    for _ in range(4):
+        out = ops.attention(q, k, v, rel_h, rel_w, grid)
+        assert torch.equal(out, ref)
+    assert torch.isfinite(ref.float()).all()

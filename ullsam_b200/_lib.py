@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libullsam_b200.so")
+LIB_PATH = os.environ.get("ULLSAM_B200_LIB") or os.path.join(_HERE, "lib", "libullsam_b200.so")
 
 OK = 0
 F32, BF16, F16 = 0, 1, 2

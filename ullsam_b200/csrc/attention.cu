@@ -12,17 +12,20 @@
 // Warp roles: QT softmax warpgroups (thread == query row == TMEM lane), one TMA producer warp, one
 // tcgen05.mma issuer warp (single thread) that also owns the TMEM allocation.
 //
-// Flash-style loop.  S = Q K^T lands in a ring of TMEM slots (3 for global, 2 for windowed) so the tensor
-// core runs ahead of the softmax; the softmax warpgroup adds the bias, exponentiates in ONE pass against a
-// stale running maximum, writes P (bf16, 128B-swizzled K-major) to shared memory and signals the MMA warp,
-// which accumulates O += P V in TMEM (V is the MN-major operand).  The running maximum is refreshed lazily:
-// when a tile's maximum exceeds the reference by more than 2^8 the row's O and sum are rescaled before the
-// next tile (exact: softmax is invariant to the reference point), and a tile whose exponent would leave the
-// fp32-safe range is simply redone with the refreshed reference.
+// Flash-style loop, everything between the two MMAs stays in tensor memory:
+//   S = Q K^T            SS MMA into a ring of TMEM slots (3 global / 2 windowed): the tensor core runs ahead
+//   softmax warpgroup    loads its whole S row (tcgen05.ld), adds the bias, takes the exact row max,
+//                        exponentiates, and stores P as packed bf16 pairs over the first half of the SAME
+//                        slot (tcgen05.st) — no shared-memory round trip
+//   O += P V             TS MMA: A = P from TMEM, B = V from shared memory (MN-major), O accumulates in TMEM
+// The running max is only moved when it grows by more than 2^8 (exact: softmax is invariant to the reference
+// point; O and the row sum are rescaled together), so touching O between tiles is rare and the softmax of
+// tile j+1 never waits for the PV MMA of tile j.
 //
 // Bias: the prologue computes Tw = Q rel_pos_w^T and Th = Q rel_pos_h^T with two extra MMAs per query tile
-// (tables zero-padded to NREL rows); each thread gathers its own 2*GRID values through a shared-memory
-// scatter, keeps rel_w (and, windowed, rel_h) in registers and (global) parks rel_h as half2 in shared memory.
+// (tables zero-padded to NREL rows) and every thread scatters its own 2*GRID values into shared memory
+// (global: rel_w fp32 in [kw/4][row][4] order for conflict-free 16-byte reads, rel_h as halves) or keeps them
+// in registers (windowed).
 #include "attention.h"
 
 #include "common.cuh"
@@ -45,23 +48,27 @@ struct AttCfg {
   static constexpr int BN = RPT * GRID;                   // keys per tile: 128 / 112
   static constexpr int NT = (T + BN - 1) / BN;            // 32 / 2
   static constexpr int NITEMS = NT * QT;                  // (tile, q-tile) work items in issue order
-  static constexpr int NSLOT = GLOBAL ? 3 : 2;            // S ring in TMEM
+  static constexpr int NSLOT = GLOBAL ? 3 : 2;            // S/P ring in TMEM, 128 columns per slot
   static constexpr int NREL = GLOBAL ? 128 : 32;          // padded rows of the rel-pos tables
   static constexpr int STAGES = GLOBAL ? 3 : 2;
   static constexpr int QBYTES = 128 * 128;                // one 128 x 64 bf16 tile
   static constexpr int KVSLOT = BN * 128;                 // one K (or V) tile: 16 KB / 14 KB
+  static constexpr int NROWS = QT * 128;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_KV = QT * QBYTES;              // STAGES x (K slot, V slot)
-  static constexpr int OFF_P = OFF_KV + STAGES * 2 * KVSLOT;   // QT x 2 k-blocks x 16 KB
-  static constexpr int OFF_RELH = OFF_P + QT * 32768;     // global: half2 rel_h [32][256]
-  static constexpr int OFF_BAR = OFF_RELH + (GLOBAL ? 32 * 256 * 4 : 0);
+  static constexpr int OFF_RELW = OFF_KV + STAGES * 2 * KVSLOT;
+  //   global  : rel_w fp32 [16][NROWS][4] (64 KB) then rel_h half [64][NROWS] (32 KB)
+  //   windowed: scatter scratch fp32 [14][NROWS] (7 KB, padded to 8 KB) then the two rel-pos tables (2 x 4 KB)
+  static constexpr int OFF_RELH = OFF_RELW + (GLOBAL ? 16 * NROWS * 16 : 8192);
+  static constexpr int OFF_BAR = OFF_RELH + (GLOBAL ? 64 * NROWS * 2 : 8192);
   static constexpr int NBAR = 3 + 2 * STAGES + NSLOT + 2 * QT;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = GLOBAL ? 512 : 256;
-  // TMEM columns.  global: S slots 0/128/256, O 384 + qt*64.  windowed: S slots 0/128, O aliases slot 0.
-  static constexpr int COL_O = GLOBAL ? 384 : 0;
+  // TMEM columns.  global: slots 0/128/256, O 384 + qt*64.  windowed: slots 0/128, O at 64 (S(0) is dead by then,
+  // P(0) only covers columns 0..55).
+  static constexpr int COL_O = GLOBAL ? 384 : 64;
   // where the rel-pos tables ride until the prologue MMAs retire
-  static constexpr int OFF_RELTAB_W = GLOBAL ? OFF_KV + (STAGES - 1) * 2 * KVSLOT : OFF_P + 16384;
+  static constexpr int OFF_RELTAB_W = GLOBAL ? OFF_KV + (STAGES - 1) * 2 * KVSLOT : OFF_RELH;
   static constexpr int OFF_RELTAB_H = GLOBAL ? OFF_RELTAB_W + KVSLOT : OFF_RELTAB_W + 4096;
 };
 
@@ -78,6 +85,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmRw, int heads, __nv_bfloat16* __restrict__ out) {
   using A = AttCfg<GRID>;
   constexpr int S = A::STAGES, BN = A::BN, NT = A::NT, QT = A::QT, NSLOT = A::NSLOT, NITEMS = A::NITEMS;
+  constexpr int NROWS = A::NROWS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A::OFF_BAR);
@@ -95,7 +103,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int gh = blockIdx.y;                       // group * heads + head
   const int qblock = blockIdx.x;                   // block of QT*128 queries inside the group
   const int row_base = gh * A::T;                  // first row of this (group, head) in q/k/v
-  const int q_row0 = row_base + qblock * (QT * 128);
+  const int q_row0 = row_base + qblock * NROWS;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -147,10 +155,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, BN, 0, 0);
       constexpr uint32_t idesc_rel = make_idesc_bf16(128, A::NREL, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // V is the MN-major B operand
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // A = P (TMEM, K-major), B = V (smem, MN-major)
       const uint32_t sq = smem_u32(smem + A::OFF_Q);
       const uint32_t skv = smem_u32(smem + A::OFF_KV);
-      const uint32_t sp = smem_u32(smem + A::OFF_P);
 
       auto issue_qk = [&](int n) {  // S[slot n % NSLOT] = Q[qt] K(j)^T
         const int j = n / QT, qt = n % QT, stage = j % S;
@@ -164,14 +171,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int k = 0; k < 4; ++k) umma_ss(tmem_base + (n % NSLOT) * 128, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
         umma_commit(&s_full[n % NSLOT]);
       };
-      auto issue_pv = [&](int n) {  // O[qt] (+)= P[qt] V(j)
+      auto issue_pv = [&](int n) {  // O[qt] (+)= P(n) V(j), P read from the first BN/2 columns of slot n % NSLOT
         const int j = n / QT, qt = n % QT, stage = j % S;
         const uint64_t dv = make_smem_desc_sw128(skv + stage * 2 * A::KVSLOT + A::KVSLOT, 16, 1024);
 #pragma unroll
         for (int s = 0; s < BN / 16; ++s) {
-          const uint64_t dp = make_smem_desc_sw128(sp + qt * 32768 + (s >> 2) * 16384, 16, 1024) + 2 * (s & 3);
-          // V tile: 16 keys further down = 16 rows x 128 B = 2048 B
-          umma_ss(tmem_base + A::COL_O + qt * 64, dp, dv + s * 128, idesc_pv, (j | s) != 0);
+          // 16 keys per step: 8 TMEM columns of packed bf16 pairs; 16 V rows x 128 B = 2048 B of shared memory
+          umma_ts(tmem_base + A::COL_O + qt * 64, tmem_base + (n % NSLOT) * 128 + s * 8, dv + s * 128, idesc_pv,
+                  (j | s) != 0);
         }
         umma_commit(&o_done[qt]);
         if (qt == QT - 1) umma_commit(&kv_empty[stage]);
@@ -195,15 +202,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       umma_commit(pro_mma_done);
-      if (!A::GLOBAL) issue_qk(0);  // windowed: slot 0 does not overlap the prologue tables (slot 1)
+      // NOTE: issuing QK(0) here, before the softmax warps have drained the prologue tables, was measured to be
+      // racy on B200 (run-to-run differences) even though the TMEM column ranges do not overlap; keep it after.
       mbar_wait(pro_consumed, 0);
       tc_fence_after();
-      for (int n = A::GLOBAL ? 0 : 1; n < NSLOT && n < NITEMS; ++n) issue_qk(n);
+      for (int n = 0; n < NSLOT && n < NITEMS; ++n) issue_qk(n);
       for (int n = 0; n < NITEMS; ++n) {
-        mbar_wait(&p_ready[n % QT], (n / QT) & 1);  // P(n) written, S(n) fully consumed -> its slot is free
+        mbar_wait(&p_ready[n % QT], (n / QT) & 1);  // P(n) is in its slot
         tc_fence_after();
-        if (n + NSLOT < NITEMS) issue_qk(n + NSLOT);
         issue_pv(n);
+        // tcgen05 ops of one thread execute in issue order: the next S may overwrite this slot once PV(n) has read it
+        if (n + NSLOT < NITEMS) issue_qk(n + NSLOT);
       }
     }
   } else if (warp < A::CTRL_WARP0) {
@@ -213,14 +222,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int r = quad * 32 + lane;           // row inside the query tile == TMEM lane
     const int tidq = qt * 128 + r;            // row inside the CTA
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const int tq = qblock * (QT * 128) + tidq;  // query index inside the group
+    const int tq = qblock * NROWS + tidq;     // query index inside the group
     const int qh = tq / GRID, qw = tq % GRID;
-    constexpr int NROWS = QT * 128;
-    float* scratch = reinterpret_cast<float*>(smem + A::OFF_P);  // [<=64][NROWS] fp32, free until the first P
-    uint32_t* relh_s = reinterpret_cast<uint32_t*>(smem + A::OFF_RELH);
+    float* relw_s = reinterpret_cast<float*>(smem + A::OFF_RELW);
+    __half* relh_s = reinterpret_cast<__half*>(smem + A::OFF_RELH);
 
-    constexpr int NW = A::GLOBAL ? 64 : 14;
-    float relw[NW];
+    float relw_reg[A::GLOBAL ? 1 : 14];
     float relh_reg[A::GLOBAL ? 1 : 14];
 
     // ------------------------------------ prologue: gather the bias rows ------------------------------
@@ -229,7 +236,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     {
       const uint32_t col_w = A::GLOBAL ? qt * 128 : 128;
       const uint32_t col_h = A::GLOBAL ? 256 + qt * 128 : 160;
-      // rel_w: Tw[row][i], i = qw - kw + GRID-1  ->  scratch[kw][row]
+      // rel_w: Tw[row][i] with i = qw - kw + GRID-1
 #pragma unroll
       for (int c = 0; c < A::NREL / 32; ++c) {
         uint32_t v[32];
@@ -238,12 +245,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int kw = qw + (GRID - 1) - (c * 32 + i);
-          if (kw >= 0 && kw < GRID) scratch[kw * NROWS + tidq] = __uint_as_float(v[i]) * kLog2e;
+          if (kw >= 0 && kw < GRID) {
+            if constexpr (A::GLOBAL) relw_s[((kw >> 2) * NROWS + tidq) * 4 + (kw & 3)] = __uint_as_float(v[i]) * kLog2e;
+            else relw_s[kw * NROWS + tidq] = __uint_as_float(v[i]) * kLog2e;
+          }
         }
       }
+      if constexpr (!A::GLOBAL) {
 #pragma unroll
-      for (int kw = 0; kw < NW; ++kw) relw[kw] = scratch[kw * NROWS + tidq];
-      // rel_h: Th[row][i], i = qh - kh + GRID-1  ->  scratch[kh][row]   (same thread re-uses its own column)
+        for (int kw = 0; kw < 14; ++kw) relw_reg[kw] = relw_s[kw * NROWS + tidq];
+      } else {
+        relw_reg[0] = 0.f;
+      }
+      // rel_h: Th[row][i] with i = qh - kh + GRID-1   (windowed: the same thread re-uses its own scratch column)
 #pragma unroll
       for (int c = 0; c < A::NREL / 32; ++c) {
         uint32_t v[32];
@@ -252,134 +266,148 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int kh = qh + (GRID - 1) - (c * 32 + i);
-          if (kh >= 0 && kh < GRID) scratch[kh * NROWS + tidq] = __uint_as_float(v[i]) * kLog2e;
+          if (kh >= 0 && kh < GRID) {
+            if constexpr (A::GLOBAL) relh_s[kh * NROWS + tidq] = __float2half_rn(__uint_as_float(v[i]) * kLog2e);
+            else relw_s[kh * NROWS + tidq] = __uint_as_float(v[i]) * kLog2e;
+          }
         }
       }
-      if constexpr (A::GLOBAL) {
+      if constexpr (!A::GLOBAL) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const __half2 h = __floats2half2_rn(scratch[(2 * j) * NROWS + tidq], scratch[(2 * j + 1) * NROWS + tidq]);
-          relh_s[j * NROWS + tidq] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        relh_reg[0] = 0.f;
+        for (int kh = 0; kh < 14; ++kh) relh_reg[kh] = relw_s[kh * NROWS + tidq];
       } else {
-#pragma unroll
-        for (int kh = 0; kh < 14; ++kh) relh_reg[kh] = scratch[kh * NROWS + tidq];
+        relh_reg[0] = 0.f;
       }
     }
     tc_fence_before();
-    // the scratch region becomes the P buffers: make sure every softmax thread is done with it
-    asm volatile("bar.sync 2, %0;" ::"n"(NROWS) : "memory");
-    if (lane == 0) mbar_arrive(pro_consumed);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(pro_consumed);  // the prologue's TMEM columns may now be overwritten
 
     // ------------------------------------ main loop ---------------------------------------------------
     const float cs = 0.125f * kLog2e;  // head_dim 64: scale = 1/8, folded with log2(e)
-    float m_used = 0.f;                // reference point of the exponentials (log2 units)
+    float m_used = -INFINITY;          // reference point of the exponentials (log2 units)
     float l = 0.f;
-    float pend = 0.f;                  // pending shift of the reference (applied before the next tile)
-    uint8_t* prow = smem + A::OFF_P + qt * 32768 + r * 128;
-    const int rx = r & 7;
     const uint32_t o_addr = lane_addr + A::COL_O + qt * 64;
-
-    // O *= 2^-shift, l *= 2^-shift, m_used += shift  (whole warp takes part: tcgen05.ld/st are collective)
-    auto shift_reference = [&](float shift, bool o_valid) {
-      const float alpha = ex2(-shift);
-      l *= alpha;
-      m_used += shift;
-      if (o_valid) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t o[32];
-          tmem_ld32(o_addr + c * 32, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(o_addr + c * 32, o);
-        }
-        tmem_wait_st();
-      }
-    };
+    constexpr int NCH = (BN + 31) / 32;  // 32-column chunks per tile (the last one is partial for BN = 112)
 
 #pragma unroll 1
     for (int j = 0; j < NT; ++j) {
       const int n = j * QT + qt;
       const uint32_t s_addr = lane_addr + (n % NSLOT) * 128;
       mbar_wait(&s_full[n % NSLOT], (n / NSLOT) & 1);
-      if (j > 0) mbar_wait(&o_done[qt], (j - 1) & 1);  // PV(j-1) retired: O is quiescent, P may be overwritten
       tc_fence_after();
-      if (__any_sync(0xffffffffu, pend != 0.f)) shift_reference(pend, j > 0);
-      pend = 0.f;
+      uint32_t v[NCH][32];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld32(s_addr + c * 32, v[c]);
+      tmem_wait_ld();
 
+      // ---- biased scores (log2 units, without the per-key-row term) and the exact row max ----
+      float mx;
       float rh0 = 0.f, rh1 = 0.f;
-      float rht[8];  // windowed: rel_h of the 8 key-grid rows of this tile
+      float rht[8];
       if constexpr (A::GLOBAL) {
-        const uint32_t hp = relh_s[j * NROWS + tidq];
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hp));
-        rh0 = f.x;
-        rh1 = f.y;
+        rh0 = __half2float(relh_s[(2 * j) * NROWS + tidq]);
+        rh1 = __half2float(relh_s[(2 * j + 1) * NROWS + tidq]);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int k4 = 0; k4 < 16; ++k4) {
+          const float4 w = *reinterpret_cast<const float4*>(relw_s + (k4 * NROWS + tidq) * 4);
+          const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int col = k4 * 4 + u;  // kw
+            const float t0 = fmaf(__uint_as_float(v[col >> 5][col & 31]), cs, wv[u]);
+            const float t1 = fmaf(__uint_as_float(v[(col + 64) >> 5][col & 31]), cs, wv[u]);
+            v[col >> 5][col & 31] = __float_as_uint(t0);
+            v[(col + 64) >> 5][col & 31] = __float_as_uint(t1);
+            mx0 = fmaxf(mx0, t0);
+            mx1 = fmaxf(mx1, t1);
+          }
+        }
+        mx = fmaxf(mx0 + rh0, mx1 + rh1);
         rht[0] = 0.f;
       } else {
 #pragma unroll
         for (int a = 0; a < 8; ++a) rht[a] = (j == 0) ? relh_reg[a] : ((8 + a < 14) ? relh_reg[(8 + a) % 14] : 0.f);
+        const int valid_cols = (j == NT - 1) ? (A::T - (NT - 1) * BN) : BN;
+        mx = -INFINITY;
+#pragma unroll
+        for (int col = 0; col < BN; ++col) {
+          float t = fmaf(__uint_as_float(v[col >> 5][col & 31]), cs, relw_reg[col % 14] + rht[col / 14]);
+          t = (col < valid_cols) ? t : -INFINITY;
+          v[col >> 5][col & 31] = __float_as_uint(t);
+          mx = fmaxf(mx, t);
+        }
       }
-      const int valid_cols = A::GLOBAL ? BN : ((j == NT - 1) ? (A::T - (NT - 1) * BN) : BN);
 
-      float amax, ls;
-      bool redo;
-      do {
-        amax = -INFINITY;
-        ls = 0.f;
-        const float c0 = rh0 - m_used, c1 = rh1 - m_used;
-        float rhm[8];
+      // ---- lazy move of the reference point (whole warp: tcgen05.ld/st are collective) ----
+      // o_done is observed exactly once per tile, in phase order (an mbarrier parity wait may never lag two
+      // phases behind): here when O has to be touched, otherwise at the end of the tile where it never stalls.
+      const bool need = mx > m_used + 8.0f;
+      bool o_seen = false;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? ex2(m_used - mx) : 1.0f;  // first tile: 2^-inf = 0, and l, O are empty
+        l *= alpha;
+        if (j > 0) {
+          mbar_wait(&o_done[qt], (j - 1) & 1);  // PV(j-1) and everything before it retired: O is quiescent
+          o_seen = true;
+          tc_fence_after();
 #pragma unroll
-        for (int a = 0; a < 8; ++a) rhm[a] = rht[a] - m_used;
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(o_addr + c * 32, o);
+            tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c * 32 >= BN) break;
-          uint32_t v[32];
-          tmem_ld32(s_addr + c * 32, v);
-          tmem_wait_ld();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int col = c * 32 + i + u;
-              p[u] = 0.f;
-              if (col < BN) {
-                float b;
-                if constexpr (A::GLOBAL) b = relw[col & 63] + ((col < 64) ? c0 : c1);
-                else b = relw[col % 14] + rhm[col / 14];
-                const float arg = fmaf(__uint_as_float(v[i + u]), cs, b);
-                if (A::GLOBAL || col < valid_cols) {
-                  amax = fmaxf(amax, arg);
-                  p[u] = ex2(arg);
-                }
-              }
-            }
-            ls += p[0] + p[1];
-            pk[i >> 1] = pack_bf16(p[0], p[1]);
-          }
-          uint8_t* dst = prow + (c >> 1) * 16384;
-          const int cc0 = (c & 1) * 4;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (c * 32 + u * 8 < BN)
-              *reinterpret_cast<uint4*>(dst + (((cc0 + u) ^ rx) << 4)) =
-                  make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(o_addr + c * 32, o);
           }
         }
-        // exponent outside the fp32-safe range (only plausible on the first tile): refresh and redo the tile
-        const bool bad = (amax > 100.f) || (j == 0 && amax < -100.f);
-        redo = __any_sync(0xffffffffu, bad);
-        if (redo) shift_reference(bad ? amax : 0.f, j > 0);
-      } while (redo);
-      l += ls;
-      // lazy refresh of the reference: on the first tile in both directions, later only upwards
-      if (amax > 8.f || (j == 0 && amax < -8.f)) pend = amax;
+        if (need) m_used = mx;
+      }
 
-      fence_proxy_async_smem();
+      // ---- P = 2^(t - m), row sum, packed bf16 pairs back into the first half of the slot ----
+      float ls0 = 0.f, ls1 = 0.f;
+      if constexpr (A::GLOBAL) {
+        const float c0 = rh0 - m_used, c1 = rh1 - m_used;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const float cc = (c < 2) ? c0 : c1;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2(__uint_as_float(v[c][i]) + cc);
+            const float p1 = ex2(__uint_as_float(v[c][i + 1]) + cc);
+            ls0 += p0;
+            ls1 += p1;
+            v[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const int col = c * 32 + i;
+            if (col < BN) {
+              const float p0 = ex2(__uint_as_float(v[c][i]) - m_used);
+              const float p1 = ex2(__uint_as_float(v[c][i + 1]) - m_used);
+              ls0 += p0;
+              ls1 += p1;
+              v[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
+            }
+          }
+        }
+      }
+      l += ls0 + ls1;
+      tmem_st32(s_addr, v[0]);
+      if constexpr (A::GLOBAL) {
+        tmem_st32(s_addr + 32, v[1]);
+      } else {
+        // BN = 112: packed columns 32..55
+        tmem_st16(s_addr + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[1][0]));
+        tmem_st8(s_addr + 48, *reinterpret_cast<uint32_t(*)[8]>(&v[1][16]));
+      }
+      tmem_wait_st();
+      if (j > 0 && !o_seen) mbar_wait(&o_done[qt], (j - 1) & 1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[qt]);
@@ -445,7 +473,7 @@ const char* launch_t(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     if (ce != cudaSuccess) return cudaGetErrorString(ce);
     configured = true;
   }
-  dim3 grid((A::T + A::QT * 128 - 1) / (A::QT * 128), G * heads);
+  dim3 grid((A::T + A::NROWS - 1) / A::NROWS, G * heads);
   kern<<<grid, A::THREADS, A::TOTAL, stream>>>(tq, tk, tv, trh, trw, heads, out);
   cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? nullptr : cudaGetErrorString(ce);
