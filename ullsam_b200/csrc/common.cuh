@@ -260,7 +260,31 @@ ULLSAM_DEVICE uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-ULLSAM_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-erf GELU (nn.GELU() default, common.py:18,23).  erf by Abramowitz & Stegun 7.1.28:
+//   erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16,  |error| <= 3e-7 for z >= 0, odd extension for z < 0
+// — one MUFU.RCP and ~15 FMA-pipe instructions instead of erff()'s two divergent branches; the error is far
+// below the bf16 rounding of the epilogue's output (and below fp32 accumulation noise of the GEMM itself).
+ULLSAM_DEVICE float erf_as(float z) {
+  const float a = fabsf(z);
+  float p = fmaf(a, 0.0000430638f, 0.0002765672f);
+  p = fmaf(p, a, 0.0001520143f);
+  p = fmaf(p, a, 0.0092705272f);
+  p = fmaf(p, a, 0.0422820123f);
+  p = fmaf(p, a, 0.0705230784f);
+  p = fmaf(p, a, 1.0f);
+  p *= p;  // ^2
+  p *= p;  // ^4
+  p *= p;  // ^8
+  p *= p;  // ^16 (overflows to +inf for |z| > ~12: 1/inf = 0, erf = 1)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+  return copysignf(1.0f - r, z);
+}
+
+ULLSAM_DEVICE float gelu_erf(float x) {
+  const float hx = 0.5f * x;
+  return fmaf(hx, erf_as(x * 0.70710678118654752440f), hx);
+}
 
 ULLSAM_DEVICE float warp_sum(float v) {
 #pragma unroll

@@ -34,7 +34,10 @@ struct GemmSmem {
   static constexpr int kBarOffset = kStages * kStageBytes;
   // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem ptr, LN scratch (2 x 2 x 128 floats)
   static constexpr int kScratchOffset = kBarOffset + (2 * kStages + 4) * 8 + 16;
-  static constexpr int kTotal = kScratchOffset + 4 * 128 * 4 + 1024 /* alignment slack */;
+  // warp-private transpose tiles of the generic epilogues: 32 rows x 80-byte pitch per epilogue warp
+  static constexpr int kStageBytesPerWarp = 32 * 80;
+  static constexpr int kStageOffset = (kScratchOffset + 4 * 128 * 4 + 15) / 16 * 16;
+  static constexpr int kTotal = kStageOffset + 8 * kStageBytesPerWarp + 1024 /* alignment slack */;
 };
 
 template <int BN, int EPI>
@@ -352,12 +355,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       } else {
+        // ---- generic epilogues.  The accumulator arrives row-per-thread (TMEM lane == row); it is transposed
+        // through a warp-private shared-memory tile so that every global access is a run of full 32-byte sectors
+        // (4 lanes cover 64 contiguous bytes of one row, 8 rows per instruction) instead of 32 scattered rows. ----
+        uint8_t* stage = smem + L::kStageOffset + (warp - GEMM_EPI_WARP0) * L::kStageBytesPerWarp;
+        const int tile_row0 = m_blk * GEMM_BM + quad * 32;
+        const int rr = lane >> 2, cc = lane & 3;  // transposed phase: row-in-group, 16-byte column slot
 #pragma unroll 1
         for (int c = 0; c < NCHUNK; ++c) {
+          const int n0 = col0 + c * 32;
+          // The addend (residual stream / pos_embed) of the whole 32-column chunk is requested before the TMEM
+          // load, so 8 independent 16-byte loads per lane are in flight while the accumulator is transposed.
+          float4 add[2][4];
+          if constexpr (EPI == EPI_RES_F32 || EPI == EPI_PATCH) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int grow = tile_row0 + it * 8 + rr;
+                add[h][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (grow < p.M) {
+                  if constexpr (EPI == EPI_RES_F32)
+                    add[h][it] = *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(grow) * p.ldc + n0 + h * 16 + cc * 4);
+                  else
+                    add[h][it] = __ldg(reinterpret_cast<const float4*>(
+                        p.pos + static_cast<size_t>(grow % p.pos_rows) * p.N + n0 + h * 16 + cc * 4));
+                }
+              }
+          }
           uint32_t v[32];
           tmem_ld32(taddr0 + c * 32, v);
           tmem_wait_ld();
-          const int n0 = col0 + c * 32;
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -385,45 +413,62 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
           }
-          if (!row_ok) continue;
-          if constexpr (EPI == EPI_BF16) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldc + n0);
+          if constexpr (EPI == EPI_BF16 || EPI == EPI_QKV) {
+            // 32 bf16 per row = 64 bytes; staged with an 80-byte row pitch (conflict-free both ways)
+            uint4* srow = reinterpret_cast<uint4*>(stage + lane * 80);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                  pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-          } else if constexpr (EPI == EPI_F32) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc + n0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else if constexpr (EPI == EPI_RES_F32) {
-            const float4* res = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(row) * p.ldc + n0);
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc + n0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 r = res[j];
-              dst[j] = make_float4(f[4 * j] + r.x, f[4 * j + 1] + r.y, f[4 * j + 2] + r.z, f[4 * j + 3] + r.w);
+              srow[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                   pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+            __syncwarp();
+            int which = 0, head = 0, d0 = 0;
+            if constexpr (EPI == EPI_QKV) {
+              const int dim = p.heads * 64;
+              which = n0 / dim;
+              const int rem = n0 - which * dim;
+              head = rem >> 6;
+              d0 = rem & 63;
             }
-          } else if constexpr (EPI == EPI_PATCH) {
-            const float4* pos = reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(row % p.pos_rows) * p.N + n0);
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc + n0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 r = __ldg(pos + j);
-              dst[j] = make_float4(f[4 * j] + r.x, f[4 * j + 1] + r.y, f[4 * j + 2] + r.z, f[4 * j + 3] + r.w);
+            for (int it = 0; it < 4; ++it) {
+              const int r_in = it * 8 + rr;
+              const int grow = tile_row0 + r_in;
+              const uint4 val = *reinterpret_cast<const uint4*>(stage + r_in * 80 + cc * 16);
+              if (grow < p.M) {
+                if constexpr (EPI == EPI_BF16) {
+                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(grow) * p.ldc + n0 + cc * 8) = val;
+                } else {
+                  const int g = grow / p.T, t = grow - g * p.T;
+                  __nv_bfloat16* base = which == 0 ? p.q : (which == 1 ? p.k : p.v);
+                  *reinterpret_cast<uint4*>(base + ((static_cast<size_t>(g) * p.heads + head) * p.T + t) * 64 + d0 + cc * 8) = val;
+                }
+              }
             }
-          } else if constexpr (EPI == EPI_QKV) {
-            const int dim = p.heads * 64;
-            const int which = n0 / dim;
-            const int rem = n0 - which * dim;
-            const int head = rem >> 6, d0 = rem & 63;
-            const int g = row / p.T, t = row - g * p.T;
-            __nv_bfloat16* base = which == 0 ? p.q : (which == 1 ? p.k : p.v);
-            uint4* dst = reinterpret_cast<uint4*>(base + ((static_cast<size_t>(g) * p.heads + head) * p.T + t) * 64 + d0);
+            __syncwarp();
+          } else {
+            // fp32 outputs: two 16-column halves, 64 bytes per row each, same 80-byte pitch
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                  pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+            for (int h = 0; h < 2; ++h) {
+              float4* srow = reinterpret_cast<float4*>(stage + lane * 80);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                srow[j] = make_float4(f[h * 16 + 4 * j], f[h * 16 + 4 * j + 1], f[h * 16 + 4 * j + 2], f[h * 16 + 4 * j + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int r_in = it * 8 + rr;
+                const int grow = tile_row0 + r_in;
+                float4 val = *reinterpret_cast<const float4*>(stage + r_in * 80 + cc * 16);
+                if (grow < p.M) {
+                  const size_t off = static_cast<size_t>(grow) * p.ldc + n0 + h * 16 + cc * 4;
+                  if constexpr (EPI == EPI_RES_F32 || EPI == EPI_PATCH) {
+                    val.x += add[h][it].x; val.y += add[h][it].y; val.z += add[h][it].z; val.w += add[h][it].w;
+                  }
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = val;
+                }
+              }
+              __syncwarp();
+            }
           }
         }
       }
