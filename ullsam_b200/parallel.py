@@ -1,0 +1,66 @@
+"""Data-parallel plumbing for the SAM path: one process per GPU, weights replicated, image batch sharded.
+
+The path has no cross-image operation, so ranks never exchange anything while computing; the only
+collective is the final all-gather of mask logits / IoU scores (and, optionally, embeddings).  ``torch.distributed``
+is used as-is: backend "nccl" on the GPU box (NVLink 5 / NVSwitch), "gloo" in the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of ``n_items`` owned by ``rank``; the first ``n_items % world`` ranks get one more."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n_items: int, world: int) -> List[int]:
+    return [shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world)]
+
+
+def gather_batch(local: torch.Tensor, n_items: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """All-gather per-rank shards (dim 0 sized by ``shard_range``) back into the full batch, in rank order.
+    Equal shards use one ``all_gather_into_tensor``; ragged shards are padded to the largest one first."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return local
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(n_items, world)
+    if local.shape[0] != sizes[dist.get_rank(group)]:
+        raise ValueError(f"rank {dist.get_rank(group)} holds {local.shape[0]} items, expected {sizes[dist.get_rank(group)]}")
+    mx = max(sizes)
+    if min(sizes) == mx:
+        out = local.new_empty((world * mx,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    padded = local.new_zeros((mx,) + tuple(local.shape[1:]))
+    padded[: local.shape[0]] = local
+    out = local.new_empty((world * mx,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * mx: r * mx + s] for r, s in enumerate(sizes)], dim=0)
+
+
+def segment_sharded(engine, images: torch.Tensor, image_pe: torch.Tensor, sparse: torch.Tensor, dense: torch.Tensor,
+                    multimask_output: bool, group: Optional[dist.ProcessGroup] = None, gather_embeddings: bool = False):
+    """Every rank passes the SAME global batch description (``images`` may be any tensor whose dim 0 is the global
+    batch, typically a host tensor); each rank encodes + decodes only its slice and the results are all-gathered.
+    Returns (masks, iou[, embeddings]) for the whole batch on every rank."""
+    n = images.shape[0]
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    lo, hi = shard_range(n, rank, world)
+    dev = engine.device
+    emb = engine.encoder_forward(images[lo:hi].to(dev, non_blocking=True))
+    d = dense if dense.shape[0] == 1 else dense[lo:hi]
+    masks, iou = engine.decoder_forward(emb, image_pe.to(dev), sparse[lo:hi].to(dev), d.to(dev), multimask_output,
+                                        prompts_per_image=1)
+    out = (gather_batch(masks, n, group), gather_batch(iou, n, group))
+    if gather_embeddings:
+        out = out + (gather_batch(emb, n, group),)
+    return out
