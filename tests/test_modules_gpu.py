@@ -76,7 +76,7 @@ def test_weight_change_is_picked_up(ctx):
         b = enc(ctx["images"][:1])
         enc.neck[3].bias.sub_(1.0)
         c = enc(ctx["images"][:1])
-    assert torch.allclose(b, a + 1.0, atol=1e-5) and torch.equal(c, a)
+    assert torch.allclose(b, a + 1.0, atol=1e-5) and torch.allclose(c, a, atol=1e-5)  # (x + 1) - 1 != x bitwise
 
 
 def test_bf16_model_like_the_reference_app(ctx):

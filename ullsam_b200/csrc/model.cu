@@ -396,6 +396,9 @@ void register_decoder(ullsam_handle* h) {
     reg_plain<float>(h, ip + "weight", {out, in}, 1, &h->iou_w[i]);
     reg_plain<float>(h, ip + "bias", {out}, 1, &h->iou_b[i]);
   }
+  // class 1 = TwoWayTransformer tensors, class 2 = the rest of MaskDecoder (a stand-alone transformer needs only 1)
+  for (auto& kv : h->slots)
+    if (kv.second.which == 1 && kv.first.rfind("mask_decoder.transformer.", 0) != 0) kv.second.which = 2;
 }
 
 int check_ready(ullsam_handle* h, int which) {
@@ -656,6 +659,7 @@ int decoder_run(ullsam_handle* h, const float* emb, int n_img, const float* imag
                 cudaStream_t st) {
   const auto& c = h->cfg;
   if (int rc = check_ready(h, 1)) return rc;
+  if (int rc = check_ready(h, 2)) return rc;
   if (n_img <= 0 || P <= 0 || Ns < 0) return fail(h, ULLSAM_ERR_INVALID, "decoder: n_img, P must be positive");
   const int R = n_img * P, nm = c.num_mask_tokens, Nt = 1 + nm + Ns, sms = h->sms;
   if (Nt > 64) return fail(h, ULLSAM_ERR_INVALID, "decoder: more than 64 prompt tokens per prompt is not supported");
@@ -811,8 +815,10 @@ int ullsam_set_weight(ullsam_handle* h, const char* key, const void* data, int d
 int ullsam_missing_weights(const ullsam_handle* h, int which) {
   if (!h) return -1;
   int missing = 0;
-  for (auto& kv : h->slots)
-    if (kv.second.which == which && !kv.second.loaded) ++missing;
+  for (auto& kv : h->slots) {
+    const int w = kv.second.which == 2 ? 1 : kv.second.which;  // public classes: 0 encoder, 1 decoder
+    if (w == which && !kv.second.loaded) ++missing;
+  }
   return missing;
 }
 
@@ -930,6 +936,7 @@ int ullsam_segment_host(ullsam_handle* h, const float* images_host, int B, const
   if (h->cfg.depth <= 0) return fail(h, ULLSAM_ERR_STATE, "segment_host: this handle was created without an encoder (depth 0)");
   if (int rc = check_ready(h, 0)) return rc;
   if (int rc = check_ready(h, 1)) return rc;
+  if (int rc = check_ready(h, 2)) return rc;
   CKC(cudaSetDevice(h->device));
   const int cnt = multimask ? 3 : 1;
   const size_t img = static_cast<size_t>(3) * 1024 * 1024;
