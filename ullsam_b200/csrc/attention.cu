@@ -7,10 +7,11 @@
 // the zero-padded rows of edge windows carry k = v = qkv.bias and are attended to, :168-172, 243-264).
 //
 // CTA = QT query tiles of 128 rows of one (group, head):
-//   global   (GRID 64): QT = 2, 384 threads, one CTA per SM, 32 key tiles of 128 keys (2 grid rows)
-//   windowed (GRID 14): QT = 1, 192 threads, two CTAs per SM, 2 key tiles of 112 keys (8 grid rows)
-// Warp roles: QT softmax warpgroups (thread == query row == TMEM lane), one TMA producer warp, one
-// tcgen05.mma issuer warp (single thread) that also owns the TMEM allocation.
+//   global   (GRID 64): QT = 2, 640 threads, one CTA per SM, 32 key tiles of 128 keys (2 grid rows)
+//   windowed (GRID 14): QT = 1, 320 threads, two CTAs per SM, 2 key tiles of 112 keys (8 grid rows)
+// Warp roles: 8 softmax warps per query tile (TWO threads per query row, each owning half of the S tile's
+// columns, so 4-5 warps per SM sub-partition hide the MUFU / TMEM latencies with <= 96 registers and no spills),
+// one TMA producer warp, one tcgen05.mma issuer warp (single thread) that also owns the TMEM allocation.
 //
 // Flash-style loop, everything between the two MMAs stays in tensor memory:
 //   S = Q K^T            SS MMA into a ring of TMEM slots (3 global / 2 windowed): the tensor core runs ahead
@@ -41,8 +42,9 @@ template <int GRID>
 struct AttCfg {
   static constexpr bool GLOBAL = (GRID == 64);
   static constexpr int QT = GLOBAL ? 2 : 1;               // query tiles per CTA
-  static constexpr int THREADS = GLOBAL ? 384 : 192;
-  static constexpr int CTRL_WARP0 = QT * 4;               // first control warp (TMA); +1 = MMA
+  static constexpr int SM_WARPS = QT * 8;                 // softmax warps: 2 threads per query row (one per half tile)
+  static constexpr int CTRL_WARP0 = SM_WARPS;             // first control warp (TMA); +1 = MMA
+  static constexpr int THREADS = (SM_WARPS + (GLOBAL ? 4 : 2)) * 32;   // 640 / 320
   static constexpr int T = GRID * GRID;
   static constexpr int RPT = GLOBAL ? 2 : 8;              // key-grid rows per tile
   static constexpr int BN = RPT * GRID;                   // keys per tile: 128 / 112
@@ -50,26 +52,30 @@ struct AttCfg {
   static constexpr int NITEMS = NT * QT;                  // (tile, q-tile) work items in issue order
   static constexpr int NSLOT = GLOBAL ? 3 : 2;            // S/P ring in TMEM, 128 columns per slot
   static constexpr int NREL = GLOBAL ? 128 : 32;          // padded rows of the rel-pos tables
-  static constexpr int STAGES = GLOBAL ? 3 : 2;
+  static constexpr int KSTAGES = GLOBAL ? 3 : 2;          // K is needed one tile ahead of V (the S ring runs ahead)
+  static constexpr int VSTAGES = 2;
   static constexpr int QBYTES = 128 * 128;                // one 128 x 64 bf16 tile
   static constexpr int KVSLOT = BN * 128;                 // one K (or V) tile: 16 KB / 14 KB
   static constexpr int NROWS = QT * 128;
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_KV = QT * QBYTES;              // STAGES x (K slot, V slot)
-  static constexpr int OFF_RELW = OFF_KV + STAGES * 2 * KVSLOT;
+  static constexpr int OFF_K = QT * QBYTES;               // KSTAGES K tiles
+  static constexpr int OFF_V = OFF_K + KSTAGES * KVSLOT;  // VSTAGES V tiles
+  static constexpr int OFF_RELW = OFF_V + VSTAGES * KVSLOT;
   //   global  : rel_w fp32 [16][NROWS][4] (64 KB) then rel_h half [64][NROWS] (32 KB)
-  //   windowed: scatter scratch fp32 [14][NROWS] (7 KB, padded to 8 KB) then the two rel-pos tables (2 x 4 KB)
-  static constexpr int OFF_RELH = OFF_RELW + (GLOBAL ? 16 * NROWS * 16 : 8192);
-  static constexpr int OFF_BAR = OFF_RELH + (GLOBAL ? 64 * NROWS * 2 : 8192);
-  static constexpr int NBAR = 3 + 2 * STAGES + NSLOT + 2 * QT;
+  //   windowed: two scatter scratches fp32 [14][NROWS] (2 x 8 KB) then the two rel-pos tables (2 x 4 KB)
+  static constexpr int OFF_RELH = OFF_RELW + (GLOBAL ? 16 * NROWS * 16 : 16384);
+  static constexpr int OFF_XCH = OFF_RELH + (GLOBAL ? 64 * NROWS * 2 : 8192);   // row-max / row-sum exchange [2][2][NROWS] fp32
+  static constexpr int OFF_BAR = OFF_XCH + 2 * 2 * NROWS * 4;
+  static constexpr int NBAR = 3 + 2 * KSTAGES + 2 * VSTAGES + NSLOT + 2 * QT;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = GLOBAL ? 512 : 256;
   // TMEM columns.  global: slots 0/128/256, O 384 + qt*64.  windowed: slots 0/128, O at 64 (S(0) is dead by then,
   // P(0) only covers columns 0..55).
   static constexpr int COL_O = GLOBAL ? 384 : 64;
   // where the rel-pos tables ride until the prologue MMAs retire
-  static constexpr int OFF_RELTAB_W = GLOBAL ? OFF_KV + (STAGES - 1) * 2 * KVSLOT : OFF_RELH;
-  static constexpr int OFF_RELTAB_H = GLOBAL ? OFF_RELTAB_W + KVSLOT : OFF_RELTAB_W + 4096;
+  // (global: the last K slot and the last V slot; windowed: a private 8 KB region)
+  static constexpr int OFF_RELTAB_W = GLOBAL ? OFF_K + (KSTAGES - 1) * KVSLOT : OFF_RELH;
+  static constexpr int OFF_RELTAB_H = GLOBAL ? OFF_V + (VSTAGES - 1) * KVSLOT : OFF_RELTAB_W + 4096;
 };
 
 ULLSAM_DEVICE float ex2(float x) {
@@ -84,17 +90,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmRh,
                  const __grid_constant__ CUtensorMap tmRw, int heads, __nv_bfloat16* __restrict__ out) {
   using A = AttCfg<GRID>;
-  constexpr int S = A::STAGES, BN = A::BN, NT = A::NT, QT = A::QT, NSLOT = A::NSLOT, NITEMS = A::NITEMS;
+  constexpr int KS = A::KSTAGES, VS = A::VSTAGES, BN = A::BN, NT = A::NT, QT = A::QT, NSLOT = A::NSLOT, NITEMS = A::NITEMS;
   constexpr int NROWS = A::NROWS;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128B-swizzle atoms, computed as an offset so the pointer stays in the shared window
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A::OFF_BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* pro_mma_done = bars + 1;
   uint64_t* pro_consumed = bars + 2;
-  uint64_t* kv_full = bars + 3;
-  uint64_t* kv_empty = kv_full + S;
-  uint64_t* s_full = kv_empty + S;      // [NSLOT]
+  uint64_t* k_full = bars + 3;          // [KS]
+  uint64_t* k_empty = k_full + KS;
+  uint64_t* v_full = k_empty + KS;      // [VS]
+  uint64_t* v_empty = v_full + VS;
+  uint64_t* s_full = v_empty + VS;      // [NSLOT]
   uint64_t* p_ready = s_full + NSLOT;   // [QT]
   uint64_t* o_done = p_ready + QT;      // [QT]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + QT);
@@ -108,14 +117,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     mbar_init(pro_mma_done, 1);
-    mbar_init(pro_consumed, QT * 4);
-    for (int i = 0; i < S; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+    mbar_init(pro_consumed, A::SM_WARPS);
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < VS; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     for (int i = 0; i < NSLOT; ++i) mbar_init(&s_full[i], 1);
     for (int i = 0; i < QT; ++i) {
-      mbar_init(&p_ready[i], 4);
+      mbar_init(&p_ready[i], 8);
       mbar_init(&o_done[i], 1);
     }
     fence_barrier_init();
@@ -131,9 +144,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp == A::CTRL_WARP0) {
     // =========================================== TMA producer ===========================================
+    // lane 0 streams Q, the rel-pos tables and the K tiles; lane 1 streams the V tiles through their own ring
+    // (V(j) is consumed a full tile later than K(j), so one thread waiting on a V slot must not hold back K).
     if (lane == 0) {
-      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-      uint8_t* kv = smem + A::OFF_KV;
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK);
       mbar_arrive_expect_tx(q_full, QT * A::QBYTES + 2 * A::NREL * 128);
 #pragma unroll
       for (int qt = 0; qt < QT; ++qt) tma_load_2d(smem + A::OFF_Q + qt * A::QBYTES, &tmQ, q_full, 0, q_row0 + qt * 128);
@@ -142,12 +156,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < NT; ++j) {
-        if (A::GLOBAL && j == S - 1) mbar_wait(pro_mma_done, 0);  // that stage still holds the rel-pos tables
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&kv_full[stage], 2 * A::KVSLOT);
-        tma_load_2d(kv + stage * 2 * A::KVSLOT, &tmK, &kv_full[stage], 0, row_base + j * BN);
-        tma_load_2d(kv + stage * 2 * A::KVSLOT + A::KVSLOT, &tmV, &kv_full[stage], 0, row_base + j * BN);
-        if (++stage == S) { stage = 0; phase ^= 1; }
+        if (A::GLOBAL && j == KS - 1) mbar_wait(pro_mma_done, 0);  // that slot still holds the rel_w table
+        mbar_wait(&k_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&k_full[stage], A::KVSLOT);
+        tma_load_2d(smem + A::OFF_K + stage * A::KVSLOT, &tmK, &k_full[stage], 0, row_base + j * BN);
+        if (++stage == KS) { stage = 0; phase ^= 1; }
+      }
+    } else if (lane == 1) {
+      tma_prefetch_desc(&tmV);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < NT; ++j) {
+        if (A::GLOBAL && j == VS - 1) mbar_wait(pro_mma_done, 0);  // that slot still holds the rel_h table
+        mbar_wait(&v_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&v_full[stage], A::KVSLOT);
+        tma_load_2d(smem + A::OFF_V + stage * A::KVSLOT, &tmV, &v_full[stage], 0, row_base + j * BN);
+        if (++stage == VS) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == A::CTRL_WARP0 + 1) {
@@ -157,23 +181,29 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       constexpr uint32_t idesc_rel = make_idesc_bf16(128, A::NREL, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // A = P (TMEM, K-major), B = V (smem, MN-major)
       const uint32_t sq = smem_u32(smem + A::OFF_Q);
-      const uint32_t skv = smem_u32(smem + A::OFF_KV);
+      const uint32_t sk = smem_u32(smem + A::OFF_K);
+      const uint32_t sv = smem_u32(smem + A::OFF_V);
 
       auto issue_qk = [&](int n) {  // S[slot n % NSLOT] = Q[qt] K(j)^T
-        const int j = n / QT, qt = n % QT, stage = j % S;
+        const int j = n / QT, qt = n % QT, stage = j % KS;
         if (qt == 0) {
-          mbar_wait(&kv_full[stage], (j / S) & 1);
+          mbar_wait(&k_full[stage], (j / KS) & 1);
           tc_fence_after();
         }
         const uint64_t dq = make_smem_desc_sw128(sq + qt * A::QBYTES, 16, 1024);
-        const uint64_t dk = make_smem_desc_sw128(skv + stage * 2 * A::KVSLOT, 16, 1024);
+        const uint64_t dk = make_smem_desc_sw128(sk + stage * A::KVSLOT, 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_ss(tmem_base + (n % NSLOT) * 128, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
         umma_commit(&s_full[n % NSLOT]);
+        if (qt == QT - 1) umma_commit(&k_empty[stage]);  // K(j) is free once both query tiles' QK have retired
       };
       auto issue_pv = [&](int n) {  // O[qt] (+)= P(n) V(j), P read from the first BN/2 columns of slot n % NSLOT
-        const int j = n / QT, qt = n % QT, stage = j % S;
-        const uint64_t dv = make_smem_desc_sw128(skv + stage * 2 * A::KVSLOT + A::KVSLOT, 16, 1024);
+        const int j = n / QT, qt = n % QT, stage = j % VS;
+        if (qt == 0) {
+          mbar_wait(&v_full[stage], (j / VS) & 1);
+          tc_fence_after();
+        }
+        const uint64_t dv = make_smem_desc_sw128(sv + stage * A::KVSLOT, 16, 1024);
 #pragma unroll
         for (int s = 0; s < BN / 16; ++s) {
           // 16 keys per step: 8 TMEM columns of packed bf16 pairs; 16 V rows x 128 B = 2048 B of shared memory
@@ -181,7 +211,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                   (j | s) != 0);
         }
         umma_commit(&o_done[qt]);
-        if (qt == QT - 1) umma_commit(&kv_empty[stage]);
+        if (qt == QT - 1) umma_commit(&v_empty[stage]);
       };
 
       // ---- prologue: Tw[qt] = Q[qt] Rw^T, Th[qt] = Q[qt] Rh^T ----
@@ -216,79 +246,74 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else if (warp < A::CTRL_WARP0) {
-    // =========================================== softmax warpgroups =====================================
-    const int qt = warp >> 2;
+    // =========================================== softmax warps ==========================================
+    // Two threads per query row: thread (row, hs) owns columns [hs*HALF, hs*HALF + HALF) of every S tile, i.e. one
+    // key-grid row per tile for the global grid.  The pair lives in two warps of the same TMEM lane quadrant and
+    // exchanges its partial row max (every tile) and row sum (once, at the end) through shared memory.
+    const int qt = warp >> 3;
+    const int hs = (warp >> 2) & 1;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;           // row inside the query tile == TMEM lane
     const int tidq = qt * 128 + r;            // row inside the CTA
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int tq = qblock * NROWS + tidq;     // query index inside the group
     const int qh = tq / GRID, qw = tq % GRID;
+    constexpr int HALF = BN / 2;              // 64 / 56 columns per thread
     float* relw_s = reinterpret_cast<float*>(smem + A::OFF_RELW);
     __half* relh_s = reinterpret_cast<__half*>(smem + A::OFF_RELH);
+    float* xch = reinterpret_cast<float*>(smem + A::OFF_XCH);  // [parity][hs][NROWS]
+    const int bar_id = 1 + qt;                // named barrier of this query tile's 8 warps
 
     float relw_reg[A::GLOBAL ? 1 : 14];
     float relh_reg[A::GLOBAL ? 1 : 14];
 
     // ------------------------------------ prologue: gather the bias rows ------------------------------
+    // hs == 0 scatters rel_w (Tw[row][qw - kw + GRID-1]), hs == 1 scatters rel_h (Th[row][qh - kh + GRID-1]).
     mbar_wait(pro_mma_done, 0);
     tc_fence_after();
     {
       const uint32_t col_w = A::GLOBAL ? qt * 128 : 128;
       const uint32_t col_h = A::GLOBAL ? 256 + qt * 128 : 160;
-      // rel_w: Tw[row][i] with i = qw - kw + GRID-1
+      const uint32_t col_t = hs ? col_h : col_w;
+      const int q0 = hs ? qh : qw;
 #pragma unroll
       for (int c = 0; c < A::NREL / 32; ++c) {
         uint32_t v[32];
-        tmem_ld32(lane_addr + col_w + c * 32, v);
+        tmem_ld32(lane_addr + col_t + c * 32, v);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int kw = qw + (GRID - 1) - (c * 32 + i);
-          if (kw >= 0 && kw < GRID) {
-            if constexpr (A::GLOBAL) relw_s[((kw >> 2) * NROWS + tidq) * 4 + (kw & 3)] = __uint_as_float(v[i]) * kLog2e;
-            else relw_s[kw * NROWS + tidq] = __uint_as_float(v[i]) * kLog2e;
+          const int kk = q0 + (GRID - 1) - (c * 32 + i);
+          if (kk >= 0 && kk < GRID) {
+            const float val = __uint_as_float(v[i]) * kLog2e;
+            if constexpr (A::GLOBAL) {
+              if (hs) relh_s[kk * NROWS + tidq] = __float2half_rn(val);
+              else relw_s[((kk >> 2) * NROWS + tidq) * 4 + (kk & 3)] = val;
+            } else {
+              relw_s[(hs * 14 + kk) * NROWS + tidq] = val;
+            }
           }
         }
-      }
-      if constexpr (!A::GLOBAL) {
-#pragma unroll
-        for (int kw = 0; kw < 14; ++kw) relw_reg[kw] = relw_s[kw * NROWS + tidq];
-      } else {
-        relw_reg[0] = 0.f;
-      }
-      // rel_h: Th[row][i] with i = qh - kh + GRID-1   (windowed: the same thread re-uses its own scratch column)
-#pragma unroll
-      for (int c = 0; c < A::NREL / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + col_h + c * 32, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kh = qh + (GRID - 1) - (c * 32 + i);
-          if (kh >= 0 && kh < GRID) {
-            if constexpr (A::GLOBAL) relh_s[kh * NROWS + tidq] = __float2half_rn(__uint_as_float(v[i]) * kLog2e);
-            else relw_s[kh * NROWS + tidq] = __uint_as_float(v[i]) * kLog2e;
-          }
-        }
-      }
-      if constexpr (!A::GLOBAL) {
-#pragma unroll
-        for (int kh = 0; kh < 14; ++kh) relh_reg[kh] = relw_s[kh * NROWS + tidq];
-      } else {
-        relh_reg[0] = 0.f;
       }
     }
     tc_fence_before();
-    __syncwarp();
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+    if constexpr (!A::GLOBAL) {
+#pragma unroll
+      for (int k = 0; k < 14; ++k) {
+        relw_reg[k] = relw_s[k * NROWS + tidq];
+        relh_reg[k] = relw_s[(14 + k) * NROWS + tidq];
+      }
+    } else {
+      relw_reg[0] = relh_reg[0] = 0.f;
+    }
     if (lane == 0) mbar_arrive(pro_consumed);  // the prologue's TMEM columns may now be overwritten
 
     // ------------------------------------ main loop ---------------------------------------------------
     const float cs = 0.125f * kLog2e;  // head_dim 64: scale = 1/8, folded with log2(e)
-    float m_used = -INFINITY;          // reference point of the exponentials (log2 units)
-    float l = 0.f;
-    const uint32_t o_addr = lane_addr + A::COL_O + qt * 64;
-    constexpr int NCH = (BN + 31) / 32;  // 32-column chunks per tile (the last one is partial for BN = 112)
+    float m_used = -INFINITY;          // reference point of the exponentials (log2 units), identical in the pair
+    float l = 0.f;                     // partial row sum (this thread's columns)
+    const uint32_t o_addr = lane_addr + A::COL_O + qt * 64 + hs * 32;  // this thread's 32 of the 64 O columns
 
 #pragma unroll 1
     for (int j = 0; j < NT; ++j) {
@@ -296,19 +321,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t s_addr = lane_addr + (n % NSLOT) * 128;
       mbar_wait(&s_full[n % NSLOT], (n / NSLOT) & 1);
       tc_fence_after();
-      uint32_t v[NCH][32];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) tmem_ld32(s_addr + c * 32, v[c]);
+      uint32_t v[2][32];
+      tmem_ld32(s_addr + hs * HALF, v[0]);
+      tmem_ld32(s_addr + hs * HALF + 32, v[1]);  // windowed: only the first HALF - 32 = 24 columns are used
       tmem_wait_ld();
 
-      // ---- biased scores (log2 units, without the per-key-row term) and the exact row max ----
-      float mx;
-      float rh0 = 0.f, rh1 = 0.f;
-      float rht[8];
+      // ---- biased scores (log2 units) and this half's row max ----
+      float mxp = -INFINITY;
+      float rh = 0.f;
       if constexpr (A::GLOBAL) {
-        rh0 = __half2float(relh_s[(2 * j) * NROWS + tidq]);
-        rh1 = __half2float(relh_s[(2 * j + 1) * NROWS + tidq]);
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        rh = __half2float(relh_s[(2 * j + hs) * NROWS + tidq]);
 #pragma unroll
         for (int k4 = 0; k4 < 16; ++k4) {
           const float4 w = *reinterpret_cast<const float4*>(relw_s + (k4 * NROWS + tidq) * 4);
@@ -316,29 +338,36 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int col = k4 * 4 + u;  // kw
-            const float t0 = fmaf(__uint_as_float(v[col >> 5][col & 31]), cs, wv[u]);
-            const float t1 = fmaf(__uint_as_float(v[(col + 64) >> 5][col & 31]), cs, wv[u]);
-            v[col >> 5][col & 31] = __float_as_uint(t0);
-            v[(col + 64) >> 5][col & 31] = __float_as_uint(t1);
-            mx0 = fmaxf(mx0, t0);
-            mx1 = fmaxf(mx1, t1);
+            const float t = fmaf(__uint_as_float(v[col >> 5][col & 31]), cs, wv[u]);
+            v[col >> 5][col & 31] = __float_as_uint(t);
+            mxp = fmaxf(mxp, t);
           }
         }
-        mx = fmaxf(mx0 + rh0, mx1 + rh1);
-        rht[0] = 0.f;
+        mxp += rh;
       } else {
+        // columns hs*56 + i: key-grid row j*8 + hs*4 + i/14, key-grid column i % 14 (56 = 4 * 14)
+        float rht[4];
 #pragma unroll
-        for (int a = 0; a < 8; ++a) rht[a] = (j == 0) ? relh_reg[a] : ((8 + a < 14) ? relh_reg[(8 + a) % 14] : 0.f);
-        const int valid_cols = (j == NT - 1) ? (A::T - (NT - 1) * BN) : BN;
-        mx = -INFINITY;
+        for (int a4 = 0; a4 < 4; ++a4) {
+          const int kh = j * 8 + hs * 4 + a4;
+          float x = 0.f;
 #pragma unroll
-        for (int col = 0; col < BN; ++col) {
-          float t = fmaf(__uint_as_float(v[col >> 5][col & 31]), cs, relw_reg[col % 14] + rht[col / 14]);
-          t = (col < valid_cols) ? t : -INFINITY;
-          v[col >> 5][col & 31] = __float_as_uint(t);
-          mx = fmaxf(mx, t);
+          for (int k = 0; k < 14; ++k) x = (k == kh) ? relh_reg[k] : x;
+          rht[a4] = x;
+        }
+        const int valid = ((j == NT - 1) ? (A::T - (NT - 1) * BN) : BN) - hs * HALF;  // valid columns of this half
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) {
+          float t = fmaf(__uint_as_float(v[i >> 5][i & 31]), cs, relw_reg[i % 14] + rht[i / 14]);
+          t = (i < valid) ? t : -INFINITY;
+          v[i >> 5][i & 31] = __float_as_uint(t);
+          mxp = fmaxf(mxp, t);
         }
       }
+      // ---- exchange with the other half of the row ----
+      xch[((j & 1) * 2 + hs) * NROWS + tidq] = mxp;
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+      const float mx = fmaxf(mxp, xch[((j & 1) * 2 + (hs ^ 1)) * NROWS + tidq]);
 
       // ---- lazy move of the reference point (whole warp: tcgen05.ld/st are collective) ----
       // o_done is observed exactly once per tile, in phase order (an mbarrier parity wait may never lag two
@@ -352,59 +381,35 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait(&o_done[qt], (j - 1) & 1);  // PV(j-1) and everything before it retired: O is quiescent
           o_seen = true;
           tc_fence_after();
+          uint32_t o[32];
+          tmem_ld32(o_addr, o);
+          tmem_wait_ld();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld32(o_addr + c * 32, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(o_addr + c * 32, o);
-          }
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(o_addr, o);
         }
         if (need) m_used = mx;
       }
 
-      // ---- P = 2^(t - m), row sum, packed bf16 pairs back into the first half of the slot ----
+      // ---- P = 2^(t - m), partial row sum, packed bf16 pairs back into the first half of the slot ----
       float ls0 = 0.f, ls1 = 0.f;
-      if constexpr (A::GLOBAL) {
-        const float c0 = rh0 - m_used, c1 = rh1 - m_used;
+      const float cc = rh - m_used;  // windowed: rh == 0 (already folded into t)
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const float cc = (c < 2) ? c0 : c1;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2(__uint_as_float(v[c][i]) + cc);
-            const float p1 = ex2(__uint_as_float(v[c][i + 1]) + cc);
-            ls0 += p0;
-            ls1 += p1;
-            v[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const int col = c * 32 + i;
-            if (col < BN) {
-              const float p0 = ex2(__uint_as_float(v[c][i]) - m_used);
-              const float p1 = ex2(__uint_as_float(v[c][i + 1]) - m_used);
-              ls0 += p0;
-              ls1 += p1;
-              v[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
-            }
-          }
-        }
+      for (int i = 0; i < HALF; i += 2) {
+        const float p0 = ex2(__uint_as_float(v[i >> 5][i & 31]) + cc);
+        const float p1 = ex2(__uint_as_float(v[(i + 1) >> 5][(i + 1) & 31]) + cc);
+        ls0 += p0;
+        ls1 += p1;
+        v[0][i >> 1] = pack_bf16(p0, p1);  // element i>>1 <= i has already been consumed
       }
       l += ls0 + ls1;
-      tmem_st32(s_addr, v[0]);
       if constexpr (A::GLOBAL) {
-        tmem_st32(s_addr + 32, v[1]);
+        tmem_st32(s_addr + hs * 32, v[0]);
       } else {
-        // BN = 112: packed columns 32..55
-        tmem_st16(s_addr + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[1][0]));
-        tmem_st8(s_addr + 48, *reinterpret_cast<uint32_t(*)[8]>(&v[1][16]));
+        // 28 packed columns per half
+        tmem_st16(s_addr + hs * 28, *reinterpret_cast<uint32_t(*)[16]>(&v[0][0]));
+        tmem_st8(s_addr + hs * 28 + 16, *reinterpret_cast<uint32_t(*)[8]>(&v[0][16]));
+        tmem_st4(s_addr + hs * 28 + 24, *reinterpret_cast<uint32_t(*)[4]>(&v[0][24]));
       }
       tmem_wait_st();
       if (j > 0 && !o_seen) mbar_wait(&o_done[qt], (j - 1) & 1);
@@ -414,6 +419,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
 
     // ------------------------------------ epilogue: O / l -> out ---------------------------------------
+    xch[((NT & 1) * 2 + hs) * NROWS + tidq] = l;
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+    l += xch[((NT & 1) * 2 + (hs ^ 1)) * NROWS + tidq];
     mbar_wait(&o_done[qt], (NT - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l;
@@ -429,13 +437,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
     const int head = gh % heads;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t o[32];
-      tmem_ld32(o_addr + c * 32, o);
+      tmem_ld32(o_addr, o);
       tmem_wait_ld();
       if (out_row >= 0) {
-        uint4* dst = reinterpret_cast<uint4*>(out + (out_row * heads + head) * 64 + c * 32);
+        uint4* dst = reinterpret_cast<uint4*>(out + (out_row * heads + head) * 64 + hs * 32);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           dst[u] = make_uint4(pack_bf16(__uint_as_float(o[8 * u]) * inv_l, __uint_as_float(o[8 * u + 1]) * inv_l),
