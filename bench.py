@@ -31,6 +31,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: keep NCCL's version / debug banner off it
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "images/sec/GPU SAM ViT-B enc+dec @1024² bf16; tensor-pipe util %; 1/2/4/8 GPU"
 
