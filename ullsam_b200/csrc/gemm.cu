@@ -3,6 +3,7 @@
 
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "gemm_sm100.cuh"
@@ -53,6 +54,36 @@ const char* make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, int B, int H
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(4d) failed";
 }
 
+// CTA-pair variant: cluster (2,1,1), one pair per 256 x 256 tile
+template <int EPI>
+static const char* launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
+                               cudaStream_t stream) {
+  using L = GemmSmem<256, 2>;
+  static bool configured = false;
+  auto kern = gemm_kernel<256, EPI, 2>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    configured = true;
+  }
+  const int tiles = ((p.M + 255) / 256) * (p.N / 256);
+  const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
 template <int BN, int EPI>
 static const char* launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                             cudaStream_t stream) {
@@ -87,8 +118,19 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
     e = make_tmap_2d_bf16(&ta, A, (uint64_t)p.M, (uint64_t)p.K, GEMM_BM, GEMM_BK);
   }
   if (e) return e;
-  e = make_tmap_2d_bf16(&tb, W, (uint64_t)p.N, (uint64_t)p.K, bn, GEMM_BK);
+  // Large plain GEMMs with 256-wide N tiles run on CTA pairs (each CTA loads only half of the W tile)
+  static const bool pair_disabled = getenv("ULLSAM_GEMM_NO_PAIR") != nullptr;
+  const bool pair = !pair_disabled && bn == 256 && !p.a_conv3 && p.M >= 4096 &&
+                    (epi == EPI_BF16 || epi == EPI_RES_F32 || epi == EPI_QKV);
+  e = make_tmap_2d_bf16(&tb, W, (uint64_t)p.N, (uint64_t)p.K, pair ? 128 : bn, GEMM_BK);
   if (e) return e;
+  if (pair) {
+    switch (epi) {
+      case EPI_BF16: return launch_pair<EPI_BF16>(ta, tb, p, num_sms, stream);
+      case EPI_RES_F32: return launch_pair<EPI_RES_F32>(ta, tb, p, num_sms, stream);
+      default: return launch_pair<EPI_QKV>(ta, tb, p, num_sms, stream);
+    }
+  }
 
 #define ULLSAM_GEMM_CASE(EPI)                                                            \
   case EPI:                                                                              \

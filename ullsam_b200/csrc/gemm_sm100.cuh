@@ -25,11 +25,15 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARP0 = 4;
 
-template <int BN>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile —
+// each CTA stages its own 128 rows of A and its own BN/2 rows of W, the leader issues one 256 x BN x 16 MMA that
+// reads both CTAs' shared memory, and each CTA's TMEM receives its 128 accumulator rows.  Halving the per-CTA W
+// traffic is what lifts the shared-memory / L2 operand-feed bound of the single-CTA kernel.
+template <int BN, int CG = 1>
 struct GemmSmem {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256 && CG == 1) ? 4 : 6;
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
-  static constexpr int kBBytes = BN * GEMM_BK * 2;
+  static constexpr int kBBytes = (BN / CG) * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
   // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem ptr, LN scratch (2 x 2 x 128 floats)
@@ -40,10 +44,12 @@ struct GemmSmem {
   static constexpr int kTotal = kStageOffset + 8 * kStageBytesPerWarp + 1024 /* alignment slack */;
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using L = GemmSmem<BN>;
+  using L = GemmSmem<BN, CG>;
+  static_assert(CG == 1 || BN == 256, "the CTA-pair kernel is built for 256-wide N tiles");
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   constexpr int S = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms, computed as an offset so the pointer stays in the shared window
@@ -59,10 +65,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_m = (p.M + CG * GEMM_BM - 1) / (CG * GEMM_BM);  // in units of CG*128 rows
   const int tiles_n = p.N / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = p.K / GEMM_BK;
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;    // tiles are dealt to CTAs (CG=1) or CTA pairs (CG=2)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -75,16 +82,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], 8 * CG);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, 512);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_2cta(tmem_ptr_smem, 512);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_ptr_smem, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync();  // peer barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -93,12 +106,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m_blk = (tile / tiles_n) * CG + cta_rank, n_blk = tile % tiles_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
+          if constexpr (CG == 2) {
+            // both CTAs' bytes are accounted on the LEADER's barrier (the MMA issuer lives there)
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_2cta(sa, &tmA, bar, kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d_2cta(sb, &tmB, bar, kb * GEMM_BK, n_blk * BN + cta_rank * (BN / 2));
+            if (++stage == S) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
           if (p.a_conv3) {
             const int cblocks = p.conv_c / GEMM_BK;
@@ -116,12 +138,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(CG * GEMM_BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -137,12 +159,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // +32 bytes along K inside the 128-byte swizzle row == +2 in the (addr >> 4) field
-            umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (CG == 2) umma_ss_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (CG == 2) umma_commit_2cta(&empty_bar[stage]);  // frees the slot in BOTH CTAs
+          else umma_commit(&empty_bar[stage]);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
+        if constexpr (CG == 2) umma_commit_2cta(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
       }
     }
   } else if (warp >= GEMM_EPI_WARP0) {
@@ -153,8 +178,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int COLS_PER_WARP = BN / 2;
     constexpr int NCHUNK = COLS_PER_WARP / 32;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+      const int m_blk = (tile / tiles_n) * CG + cta_rank, n_blk = tile % tiles_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -476,15 +501,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // release this accumulator buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync();  // the peer's shared memory / barriers stay alive until both are done
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (CG == 2) tmem_dealloc_2cta(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
