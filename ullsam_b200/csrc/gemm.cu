@@ -104,6 +104,8 @@ static const char* launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const 
 
 const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams& p, int num_sms, cudaStream_t stream) {
   if (p.M <= 0) return nullptr;
+  if (epi == EPI_BF16 && p.act == ACT_GELU && p.pos == nullptr) epi = EPI_GELU_BF16;
+  else if (epi == EPI_GELU_BF16) return "gemm: EPI_GELU_BF16 is selected internally";
   if (p.K % GEMM_BK != 0) return "gemm: K must be a multiple of 64";
   const bool ln = (epi == EPI_LN_BF16 || epi == EPI_LN_NCHW || epi == EPI_LN_RES || epi == EPI_UP1);
   int bn = (p.N % 256 == 0) ? 256 : 128;
@@ -121,12 +123,13 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
   // Large plain GEMMs with 256-wide N tiles run on CTA pairs (each CTA loads only half of the W tile)
   static const bool pair_disabled = getenv("ULLSAM_GEMM_NO_PAIR") != nullptr;
   const bool pair = !pair_disabled && bn == 256 && !p.a_conv3 && p.M >= 4096 &&
-                    (epi == EPI_BF16 || epi == EPI_RES_F32 || epi == EPI_QKV);
+                    (epi == EPI_BF16 || epi == EPI_GELU_BF16 || epi == EPI_RES_F32 || epi == EPI_QKV);
   e = make_tmap_2d_bf16(&tb, W, (uint64_t)p.N, (uint64_t)p.K, pair ? 128 : bn, GEMM_BK);
   if (e) return e;
   if (pair) {
     switch (epi) {
       case EPI_BF16: return launch_pair<EPI_BF16>(ta, tb, p, num_sms, stream);
+      case EPI_GELU_BF16: return launch_pair<EPI_GELU_BF16>(ta, tb, p, num_sms, stream);
       case EPI_RES_F32: return launch_pair<EPI_RES_F32>(ta, tb, p, num_sms, stream);
       default: return launch_pair<EPI_QKV>(ta, tb, p, num_sms, stream);
     }
@@ -138,6 +141,7 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
                      : launch_t<128, EPI>(ta, tb, p, num_sms, stream);
   switch (epi) {
     ULLSAM_GEMM_CASE(EPI_BF16)
+    ULLSAM_GEMM_CASE(EPI_GELU_BF16)
     ULLSAM_GEMM_CASE(EPI_RES_F32)
     ULLSAM_GEMM_CASE(EPI_QKV)
     ULLSAM_GEMM_CASE(EPI_PATCH)

@@ -20,6 +20,8 @@ enum EpiMode : int {
                     //   (TwoWayAttentionBlock: keys = norm4(keys + attn_out), transformer.py:178-182)
   EPI_UP1 = 8,      // ConvT(256->64,k2s2) + LayerNorm2d(64) + GELU -> bf16 NHWC [R,128,128,64]  (mask_decoder.py:54-56)
   EPI_MASK = 9,     // ConvT(64->32,k2s2) + GELU, contracted with hyper_in -> mask logits         (mask_decoder.py:57-58,144)
+  EPI_GELU_BF16 = 10,  // EPI_BF16 with the exact-erf GELU resolved at compile time (MLPBlock.lin1, common.py:21-26);
+                       // selected internally when EPI_BF16 is launched with act == ACT_GELU
 };
 // EPI_BF16 / EPI_F32 also add pos[row % pos_rows][n] when p.pos != nullptr.
 
