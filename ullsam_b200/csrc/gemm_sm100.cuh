@@ -387,6 +387,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint8_t* stage = smem + L::kStageOffset + (warp - GEMM_EPI_WARP0) * L::kStageBytesPerWarp;
         const int tile_row0 = m_blk * GEMM_BM + quad * 32;
         const int rr = lane >> 2, cc = lane & 3;  // transposed phase: row-in-group, 16-byte column slot
+        size_t qkv_row_off[4] = {0, 0, 0, 0};     // EPI_QKV: (g * heads * T + t) * 64 of the 4 rows this lane stores
+        if constexpr (EPI == EPI_QKV) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int grow = tile_row0 + it * 8 + rr;
+            const int g = grow / p.T, t = grow - g * p.T;
+            qkv_row_off[it] = (static_cast<size_t>(g) * p.heads * p.T + t) * 64;
+          }
+        }
         // The TMEM load of chunk c+1 is in flight while chunk c is processed (two register buffers, loop fully
         // unrolled).  The GELU variant keeps the rolled loop: its per-chunk body is ~600 instructions and four
         // copies of it fall out of the instruction cache (measured: 972 -> 850 TFLOP/s when unrolled).
@@ -464,13 +473,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               srow[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
                                    pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
             __syncwarp();
-            int which = 0, head = 0, d0 = 0;
+            size_t qkv_col_off = 0;
+            __nv_bfloat16* qkv_base = nullptr;
             if constexpr (EPI == EPI_QKV) {
               const int dim = p.heads * 64;
-              which = n0 / dim;
+              const int which = n0 / dim;
               const int rem = n0 - which * dim;
-              head = rem >> 6;
-              d0 = rem & 63;
+              qkv_base = which == 0 ? p.q : (which == 1 ? p.k : p.v);
+              qkv_col_off = static_cast<size_t>(rem >> 6) * p.T * 64 + (rem & 63);  // head * T * 64 + d0
             }
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
@@ -481,9 +491,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
                   *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(grow) * p.ldc + n0 + cc * 8) = val;
                 } else {
-                  const int g = grow / p.T, t = grow - g * p.T;
-                  __nv_bfloat16* base = which == 0 ? p.q : (which == 1 ? p.k : p.v);
-                  *reinterpret_cast<uint4*>(base + ((static_cast<size_t>(g) * p.heads + head) * p.T + t) * 64 + d0 + cc * 8) = val;
+                  *reinterpret_cast<uint4*>(qkv_base + qkv_row_off[it] + qkv_col_off + cc * 8) = val;
                 }
               }
             }
