@@ -66,7 +66,7 @@ struct AttCfg {
   static constexpr int OFF_RELH = OFF_RELW + (GLOBAL ? 16 * NROWS * 16 : 16384);
   static constexpr int OFF_XCH = OFF_RELH + (GLOBAL ? 64 * NROWS * 2 : 8192);   // row-max / row-sum exchange [2][2][NROWS] fp32
   static constexpr int OFF_BAR = OFF_XCH + 2 * 2 * NROWS * 4;
-  static constexpr int NBAR = 3 + 2 * KSTAGES + 2 * VSTAGES + NSLOT + 2 * QT;
+  static constexpr int NBAR = 3 + 2 * KSTAGES + 2 * VSTAGES + NSLOT + 3 * QT;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = GLOBAL ? 512 : 256;
   // TMEM columns.  global: slots 0/128/256, O 384 + qt*64.  windowed: slots 0/128, O at 64 (S(0) is dead by then,
@@ -79,9 +79,13 @@ struct AttCfg {
 };
 
 ULLSAM_DEVICE float ex2(float x) {
+#ifdef ULLSAM_PROBE_NO_MUFU
+  return fmaf(x, 1e-3f, 1.0f);  // timing probe only: takes the MUFU out of the softmax
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 template <int GRID>
@@ -105,8 +109,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* v_empty = v_full + VS;
   uint64_t* s_full = v_empty + VS;      // [NSLOT]
   uint64_t* p_ready = s_full + NSLOT;   // [QT]
-  uint64_t* o_done = p_ready + QT;      // [QT]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + QT);
+  uint64_t* o_done = p_ready + QT;      // [QT][2]: PV(j) of query tile qt commits to o_done[qt*2 + (j & 1)]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2 * QT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gh = blockIdx.y;                       // group * heads + head
@@ -129,7 +133,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int i = 0; i < NSLOT; ++i) mbar_init(&s_full[i], 1);
     for (int i = 0; i < QT; ++i) {
       mbar_init(&p_ready[i], 8);
-      mbar_init(&o_done[i], 1);
+      mbar_init(&o_done[2 * i], 1);
+      mbar_init(&o_done[2 * i + 1], 1);
     }
     fence_barrier_init();
   }
@@ -143,10 +148,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == A::CTRL_WARP0) {
-    // =========================================== TMA producer ===========================================
-    // lane 0 streams Q, the rel-pos tables and the K tiles; lane 1 streams the V tiles through their own ring
-    // (V(j) is consumed a full tile later than K(j), so one thread waiting on a V slot must not hold back K).
-    if (lane == 0) {
+    // =========================================== TMA producers ==========================================
+    // K stream (plus Q and the rel-pos tables) from this warp; the V stream has its own ring because V(j) is
+    // consumed a full tile later than K(j) — global: a separate warp, windowed (2 tiles): the same lane afterwards.
+    // One lane chosen by elect.sync issues (see the note at the MMA issuer).
+    if (elect_one_sync()) {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK);
       mbar_arrive_expect_tx(q_full, QT * A::QBYTES + 2 * A::NREL * 128);
 #pragma unroll
@@ -162,7 +168,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tma_load_2d(smem + A::OFF_K + stage * A::KVSLOT, &tmK, &k_full[stage], 0, row_base + j * BN);
         if (++stage == KS) { stage = 0; phase ^= 1; }
       }
-    } else if (lane == 1) {
+    }
+  }
+  if (warp == (A::GLOBAL ? A::CTRL_WARP0 + 2 : A::CTRL_WARP0)) {
+    if (elect_one_sync()) {
       tma_prefetch_desc(&tmV);
       int stage = 0;
       uint32_t phase = 0;
@@ -176,7 +185,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == A::CTRL_WARP0 + 1) {
     // =========================================== MMA issuer =============================================
-    if (lane == 0) {
+    // The whole warp walks the control flow and waits on the barriers; the tcgen05 instructions are issued by the
+    // lane picked by elect.sync.  (With a plain `lane == 0` branch ptxas wraps EVERY tcgen05.mma in an
+    // ELECT / BRA.U.ANY loop over the active lanes, ~20 instructions per MMA, which made this single warp the
+    // bottleneck of the whole kernel: 24 small MMAs per key tile.)
+    {
+      const bool leader = elect_one_sync();
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, BN, 0, 0);
       constexpr uint32_t idesc_rel = make_idesc_bf16(128, A::NREL, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // A = P (TMEM, K-major), B = V (smem, MN-major)
@@ -192,10 +206,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         const uint64_t dq = make_smem_desc_sw128(sq + qt * A::QBYTES, 16, 1024);
         const uint64_t dk = make_smem_desc_sw128(sk + stage * A::KVSLOT, 16, 1024);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + (n % NSLOT) * 128, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
-        umma_commit(&s_full[n % NSLOT]);
-        if (qt == QT - 1) umma_commit(&k_empty[stage]);  // K(j) is free once both query tiles' QK have retired
+          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + (n % NSLOT) * 128, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+          umma_commit(&s_full[n % NSLOT]);
+          if (qt == QT - 1) umma_commit(&k_empty[stage]);  // K(j) is free once both query tiles' QK have retired
+        }
+        __syncwarp();
       };
       auto issue_pv = [&](int n) {  // O[qt] (+)= P(n) V(j), P read from the first BN/2 columns of slot n % NSLOT
         const int j = n / QT, qt = n % QT, stage = j % VS;
@@ -204,14 +221,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc_fence_after();
         }
         const uint64_t dv = make_smem_desc_sw128(sv + stage * A::KVSLOT, 16, 1024);
+        if (leader) {
 #pragma unroll
-        for (int s = 0; s < BN / 16; ++s) {
-          // 16 keys per step: 8 TMEM columns of packed bf16 pairs; 16 V rows x 128 B = 2048 B of shared memory
-          umma_ts(tmem_base + A::COL_O + qt * 64, tmem_base + (n % NSLOT) * 128 + s * 8, dv + s * 128, idesc_pv,
-                  (j | s) != 0);
+          for (int s = 0; s < BN / 16; ++s) {
+            // 16 keys per step: 8 TMEM columns of packed bf16 pairs; 16 V rows x 128 B = 2048 B of shared memory
+            umma_ts(tmem_base + A::COL_O + qt * 64, tmem_base + (n % NSLOT) * 128 + s * 8, dv + s * 128, idesc_pv,
+                    (j | s) != 0);
+          }
+          umma_commit(&o_done[qt * 2 + (j & 1)]);
+          if (qt == QT - 1) umma_commit(&v_empty[stage]);
         }
-        umma_commit(&o_done[qt]);
-        if (qt == QT - 1) umma_commit(&v_empty[stage]);
+        __syncwarp();
       };
 
       // ---- prologue: Tw[qt] = Q[qt] Rw^T, Th[qt] = Q[qt] Rh^T ----
@@ -225,13 +245,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const uint64_t dq = make_smem_desc_sw128(sq + qt * A::QBYTES, 16, 1024);
           const uint32_t col_w = A::GLOBAL ? qt * 128 : 128;
           const uint32_t col_h = A::GLOBAL ? 256 + qt * 128 : 160;
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + col_w, dq + 2 * k, drw + 2 * k, idesc_rel, k != 0);
+            for (int k = 0; k < 4; ++k) umma_ss(tmem_base + col_w, dq + 2 * k, drw + 2 * k, idesc_rel, k != 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + col_h, dq + 2 * k, drh + 2 * k, idesc_rel, k != 0);
+            for (int k = 0; k < 4; ++k) umma_ss(tmem_base + col_h, dq + 2 * k, drh + 2 * k, idesc_rel, k != 0);
+          }
         }
       }
-      umma_commit(pro_mma_done);
+      if (leader) umma_commit(pro_mma_done);
+      __syncwarp();
       // NOTE: issuing QK(0) here, before the softmax warps have drained the prologue tables, was measured to be
       // racy on B200 (run-to-run differences) even though the TMEM column ranges do not overlap; keep it after.
       mbar_wait(pro_consumed, 0);
@@ -321,29 +344,41 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t s_addr = lane_addr + (n % NSLOT) * 128;
       mbar_wait(&s_full[n % NSLOT], (n / NSLOT) & 1);
       tc_fence_after();
+      // global: thread hs owns key-grid columns [hs*32, hs*32+32) of BOTH key-grid rows of the tile (S columns
+      // hs*32.. and 64+hs*32..), so it needs only 32 of the 64 rel_w values; windowed: columns [hs*56, hs*56+56).
       uint32_t v[2][32];
-      tmem_ld32(s_addr + hs * HALF, v[0]);
-      tmem_ld32(s_addr + hs * HALF + 32, v[1]);  // windowed: only the first HALF - 32 = 24 columns are used
+      if constexpr (A::GLOBAL) {
+        tmem_ld32(s_addr + hs * 32, v[0]);
+        tmem_ld32(s_addr + 64 + hs * 32, v[1]);
+      } else {
+        tmem_ld32(s_addr + hs * HALF, v[0]);
+        tmem_ld32(s_addr + hs * HALF + 32, v[1]);  // only the first HALF - 32 = 24 columns are used
+      }
       tmem_wait_ld();
 
-      // ---- biased scores (log2 units) and this half's row max ----
+      // ---- biased scores (log2 units) and this thread's partial row max ----
       float mxp = -INFINITY;
-      float rh = 0.f;
+      float rh0 = 0.f, rh1 = 0.f;
       if constexpr (A::GLOBAL) {
-        rh = __half2float(relh_s[(2 * j + hs) * NROWS + tidq]);
+        rh0 = __half2float(relh_s[(2 * j) * NROWS + tidq]);
+        rh1 = __half2float(relh_s[(2 * j + 1) * NROWS + tidq]);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int k4 = 0; k4 < 16; ++k4) {
-          const float4 w = *reinterpret_cast<const float4*>(relw_s + (k4 * NROWS + tidq) * 4);
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 w = *reinterpret_cast<const float4*>(relw_s + ((hs * 8 + k4) * NROWS + tidq) * 4);
           const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int col = k4 * 4 + u;  // kw
-            const float t = fmaf(__uint_as_float(v[col >> 5][col & 31]), cs, wv[u]);
-            v[col >> 5][col & 31] = __float_as_uint(t);
-            mxp = fmaxf(mxp, t);
+            const int i = k4 * 4 + u;  // key-grid column hs*32 + i
+            const float t0 = fmaf(__uint_as_float(v[0][i]), cs, wv[u]);
+            const float t1 = fmaf(__uint_as_float(v[1][i]), cs, wv[u]);
+            v[0][i] = __float_as_uint(t0);
+            v[1][i] = __float_as_uint(t1);
+            mx0 = fmaxf(mx0, t0);
+            mx1 = fmaxf(mx1, t1);
           }
         }
-        mxp += rh;
+        mxp = fmaxf(mx0 + rh0, mx1 + rh1);
       } else {
         // columns hs*56 + i: key-grid row j*8 + hs*4 + i/14, key-grid column i % 14 (56 = 4 * 14)
         float rht[4];
@@ -366,20 +401,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       // ---- exchange with the other half of the row ----
       xch[((j & 1) * 2 + hs) * NROWS + tidq] = mxp;
+#ifndef ULLSAM_PROBE_NO_XCH
       asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+#endif
       const float mx = fmaxf(mxp, xch[((j & 1) * 2 + (hs ^ 1)) * NROWS + tidq]);
 
       // ---- lazy move of the reference point (whole warp: tcgen05.ld/st are collective) ----
-      // o_done is observed exactly once per tile, in phase order (an mbarrier parity wait may never lag two
-      // phases behind): here when O has to be touched, otherwise at the end of the tile where it never stalls.
+      // PV(j) commits to o_done[qt][j & 1].  An mbarrier parity wait may never lag two phases behind, so every
+      // phase of both barriers is observed in order: routinely two tiles late (end of this loop body, where it never
+      // stalls), and exactly on time only when O really has to be touched here.
       const bool need = mx > m_used + 8.0f;
-      bool o_seen = false;
       if (__any_sync(0xffffffffu, need)) {
         const float alpha = need ? ex2(m_used - mx) : 1.0f;  // first tile: 2^-inf = 0, and l, O are empty
         l *= alpha;
         if (j > 0) {
-          mbar_wait(&o_done[qt], (j - 1) & 1);  // PV(j-1) and everything before it retired: O is quiescent
-          o_seen = true;
+          mbar_wait(&o_done[qt * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);  // PV(j-1) retired: O is quiescent
           tc_fence_after();
           uint32_t o[32];
           tmem_ld32(o_addr, o);
@@ -393,26 +429,40 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
       // ---- P = 2^(t - m), partial row sum, packed bf16 pairs back into the first half of the slot ----
       float ls0 = 0.f, ls1 = 0.f;
-      const float cc = rh - m_used;  // windowed: rh == 0 (already folded into t)
-#pragma unroll
-      for (int i = 0; i < HALF; i += 2) {
-        const float p0 = ex2(__uint_as_float(v[i >> 5][i & 31]) + cc);
-        const float p1 = ex2(__uint_as_float(v[(i + 1) >> 5][(i + 1) & 31]) + cc);
-        ls0 += p0;
-        ls1 += p1;
-        v[0][i >> 1] = pack_bf16(p0, p1);  // element i>>1 <= i has already been consumed
-      }
-      l += ls0 + ls1;
       if constexpr (A::GLOBAL) {
-        tmem_st32(s_addr + hs * 32, v[0]);
+        const float c0 = rh0 - m_used, c1 = rh1 - m_used;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2(__uint_as_float(v[0][i]) + c0);
+          const float p1 = ex2(__uint_as_float(v[0][i + 1]) + c0);
+          const float p2 = ex2(__uint_as_float(v[1][i]) + c1);
+          const float p3 = ex2(__uint_as_float(v[1][i + 1]) + c1);
+          ls0 += p0 + p2;
+          ls1 += p1 + p3;
+          v[0][i >> 1] = pack_bf16(p0, p1);  // element i>>1 <= i has already been consumed
+          v[1][i >> 1] = pack_bf16(p2, p3);
+        }
+        l += ls0 + ls1;
+        // keys hs*32.. -> packed columns hs*16..; keys 64+hs*32.. -> packed columns 32+hs*16..
+        tmem_st16(s_addr + hs * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[0][0]));
+        tmem_st16(s_addr + 32 + hs * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[1][0]));
       } else {
+#pragma unroll
+        for (int i = 0; i < HALF; i += 2) {
+          const float p0 = ex2(__uint_as_float(v[i >> 5][i & 31]) - m_used);
+          const float p1 = ex2(__uint_as_float(v[(i + 1) >> 5][(i + 1) & 31]) - m_used);
+          ls0 += p0;
+          ls1 += p1;
+          v[0][i >> 1] = pack_bf16(p0, p1);  // element i>>1 <= i has already been consumed
+        }
+        l += ls0 + ls1;
         // 28 packed columns per half
         tmem_st16(s_addr + hs * 28, *reinterpret_cast<uint32_t(*)[16]>(&v[0][0]));
         tmem_st8(s_addr + hs * 28 + 16, *reinterpret_cast<uint32_t(*)[8]>(&v[0][16]));
         tmem_st4(s_addr + hs * 28 + 24, *reinterpret_cast<uint32_t(*)[4]>(&v[0][24]));
       }
       tmem_wait_st();
-      if (j > 0 && !o_seen) mbar_wait(&o_done[qt], (j - 1) & 1);
+      if (j > 1) mbar_wait(&o_done[qt * 2 + (j & 1)], ((j - 2) >> 1) & 1);  // PV(j-2): long retired
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[qt]);
@@ -422,7 +472,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     xch[((NT & 1) * 2 + hs) * NROWS + tidq] = l;
     asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
     l += xch[((NT & 1) * 2 + (hs ^ 1)) * NROWS + tidq];
-    mbar_wait(&o_done[qt], (NT - 1) & 1);
+    mbar_wait(&o_done[qt * 2 + ((NT - 1) & 1)], ((NT - 1) >> 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     long out_row = -1;

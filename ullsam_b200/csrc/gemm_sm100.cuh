@@ -103,7 +103,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // (one lane chosen by elect.sync: with a plain `lane == 0` branch ptxas wraps every TMA / tcgen05 instruction
+    //  in an ELECT / BRA.U.ANY loop over the active lanes)
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -138,7 +140,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0 && cta_rank == 0) {
+    if (cta_rank == 0 && elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_bf16(CG * GEMM_BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
