@@ -177,3 +177,23 @@ def test_errors_are_loud(ctx):
     with pytest.raises(_lib.UllsamError):
         ctx["eng"].encoder_forward(torch.zeros(1, 3, 1024, 1024))  # CPU tensor: no CPU path
     eng.close()
+
+
+def test_vit_l_encoder_vs_oracle():
+    """BASELINE config 4: ViT-L (dim 1024, 24 blocks, 16 heads, global attention at 5/11/17/23)."""
+    from ullsam_b200.engine import Engine
+
+    cfg = O.config("vit_l")
+    sd = synth.make_state_dict(cfg, 4321)
+    eng = Engine(model="vit_l")
+    eng.load_state_dict(sd, only="image_encoder.")
+    assert eng.missing(0) == 0
+    images, _ = synth.make_images(1, 1024, seed=99)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = O.encoder_forward(sd, images, cfg)
+    emb = eng.encoder_forward(images.cuda()).cpu()
+    e = rel_l2(emb, ref)
+    print(f"ViT-L embedding rel-L2 error {e:.3e}")
+    assert e <= 1e-2
+    eng.close()
