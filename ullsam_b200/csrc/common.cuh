@@ -341,7 +341,9 @@ ULLSAM_DEVICE uint32_t pack_bf16(float lo, float hi) {
 //   erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16,  |error| <= 3e-7 for z >= 0, odd extension for z < 0
 // — one MUFU.RCP and ~15 FMA-pipe instructions instead of erff()'s two divergent branches; the error is far
 // below the bf16 rounding of the epilogue's output (and below fp32 accumulation noise of the GEMM itself).
-// returns 1 - erf(|x| / sqrt(2)) complement form: e = erf(|x|/sqrt(2)) in [0, 1]   (coefficients pre-scaled by 2^(-k/2))
+// erf(|x| / sqrt(2)) in [0, 1] (A&S 7.1.28 with the coefficients pre-scaled by 2^(-k/2)).  The 16th power and
+// the reciprocal are taken on the MUFU pipe as 2^(-16 log2 p): the epilogue that uses this is bound by the FMA pipe,
+// the special-function unit is otherwise idle, and lg2/ex2.approx are accurate to ~2^-22.
 ULLSAM_DEVICE float erf_abs_scaled(float x) {
   const float a = fabsf(x);
   float p = fmaf(a, 0.0000430638f * 0.125f, 0.0002765672f * 0.17677669529663687f);
@@ -349,13 +351,10 @@ ULLSAM_DEVICE float erf_abs_scaled(float x) {
   p = fmaf(p, a, 0.0092705272f * 0.35355339059327373f);
   p = fmaf(p, a, 0.0422820123f * 0.5f);
   p = fmaf(p, a, 0.0705230784f * 0.70710678118654752f);
-  p = fmaf(p, a, 1.0f);
-  p *= p;  // ^2
-  p *= p;  // ^4
-  p *= p;  // ^8
-  p *= p;  // ^16 (overflows to +inf for |x| > ~17: 1/inf = 0, erf = 1)
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+  p = fmaf(p, a, 1.0f);  // >= 1
+  float lg, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(p));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(lg * -16.0f));
   return 1.0f - r;
 }
 
@@ -363,6 +362,13 @@ ULLSAM_DEVICE float erf_as(float z) { return copysignf(erf_abs_scaled(z * 1.4142
 
 // gelu(x) = x/2 + |x/2| * erf(|x|/sqrt(2))   (erf is odd, so the sign rides on x/2)
 ULLSAM_DEVICE float gelu_erf(float x) {
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs_scaled(x), hx);
+}
+
+// gelu(acc + bias) with the bias add folded into the first multiply
+ULLSAM_DEVICE float gelu_erf_bias(float acc, float bias) {
+  const float x = acc + bias;
   const float hx = 0.5f * x;
   return fmaf(fabsf(hx), erf_abs_scaled(x), hx);
 }

@@ -55,12 +55,12 @@ const char* make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, int B, int H
 }
 
 // CTA-pair variant: cluster (2,1,1), one pair per 256 x 256 tile
-template <int EPI>
+template <int EPI, int EW>
 static const char* launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                                cudaStream_t stream) {
-  using L = GemmSmem<256, 2>;
+  using L = GemmSmem<256, 2, EW>;
   static bool configured = false;
-  auto kern = gemm_kernel<256, EPI, 2>;
+  auto kern = gemm_kernel<256, EPI, 2, EW>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return cudaGetErrorString(e);
@@ -70,7 +70,7 @@ static const char* launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, con
   const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3((GEMM_EPI_WARP0 + EW) * 32);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -127,11 +127,18 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
   e = make_tmap_2d_bf16(&tb, W, (uint64_t)p.N, (uint64_t)p.K, pair ? 128 : bn, GEMM_BK);
   if (e) return e;
   if (pair) {
+    static const int ew16 = getenv("ULLSAM_GEMM_EW16") ? atoi(getenv("ULLSAM_GEMM_EW16")) : 0x1;  // bit mask per epilogue
     switch (epi) {
-      case EPI_BF16: return launch_pair<EPI_BF16>(ta, tb, p, num_sms, stream);
-      case EPI_GELU_BF16: return launch_pair<EPI_GELU_BF16>(ta, tb, p, num_sms, stream);
-      case EPI_RES_F32: return launch_pair<EPI_RES_F32>(ta, tb, p, num_sms, stream);
-      default: return launch_pair<EPI_QKV>(ta, tb, p, num_sms, stream);
+      case EPI_BF16: return launch_pair<EPI_BF16, 8>(ta, tb, p, num_sms, stream);
+      case EPI_GELU_BF16:
+        return (ew16 & 1) ? launch_pair<EPI_GELU_BF16, 16>(ta, tb, p, num_sms, stream)
+                          : launch_pair<EPI_GELU_BF16, 8>(ta, tb, p, num_sms, stream);
+      case EPI_RES_F32:
+        return (ew16 & 2) ? launch_pair<EPI_RES_F32, 16>(ta, tb, p, num_sms, stream)
+                          : launch_pair<EPI_RES_F32, 8>(ta, tb, p, num_sms, stream);
+      default:
+        return (ew16 & 4) ? launch_pair<EPI_QKV, 16>(ta, tb, p, num_sms, stream)
+                          : launch_pair<EPI_QKV, 8>(ta, tb, p, num_sms, stream);
     }
   }
 

@@ -22,16 +22,16 @@ namespace ullsam {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps (the EW = 16 variant runs 640 threads)
 constexpr int GEMM_EPI_WARP0 = 4;
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile —
 // each CTA stages its own 128 rows of A and its own BN/2 rows of W, the leader issues one 256 x BN x 16 MMA that
 // reads both CTAs' shared memory, and each CTA's TMEM receives its 128 accumulator rows.  Halving the per-CTA W
 // traffic is what lifts the shared-memory / L2 operand-feed bound of the single-CTA kernel.
-template <int BN, int CG = 1>
+template <int BN, int CG = 1, int EW = 8>
 struct GemmSmem {
-  static constexpr int kStages = (BN == 256 && CG == 1) ? 4 : 6;
+  static constexpr int kStages = (BN == 256 && CG == 1) ? 4 : (EW == 16 ? 5 : 6);
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
   static constexpr int kBBytes = (BN / CG) * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -41,13 +41,17 @@ struct GemmSmem {
   // warp-private transpose tiles of the generic epilogues: 32 rows x 80-byte pitch per epilogue warp
   static constexpr int kStageBytesPerWarp = 32 * 80;
   static constexpr int kStageOffset = (kScratchOffset + 4 * 128 * 4 + 15) / 16 * 16;
-  static constexpr int kTotal = kStageOffset + 8 * kStageBytesPerWarp + 1024 /* alignment slack */;
+  static constexpr int kTotal = kStageOffset + EW * kStageBytesPerWarp + 1024 /* alignment slack */;
 };
 
-template <int BN, int EPI, int CG = 1>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// EW epilogue warps: 8 (two per TMEM lane quadrant, BN/2 columns each) or 16 (four per quadrant, BN/4 columns each:
+// twice the warps to hide the TMEM / global latencies of the epilogue and to spread the GELU arithmetic).
+template <int BN, int EPI, int CG = 1, int EW = 8>
+__global__ void __launch_bounds__((GEMM_EPI_WARP0 + EW) * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using L = GemmSmem<BN, CG>;
+  using L = GemmSmem<BN, CG, EW>;
+  static_assert(EW == 8 || (EPI != EPI_LN_BF16 && EPI != EPI_LN_NCHW && EPI != EPI_LN_RES && EPI != EPI_UP1 && EPI != EPI_MASK),
+                "the LayerNorm / decoder epilogues assume two warps per row");
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel is built for 256-wide N tiles");
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   constexpr int S = L::kStages;
@@ -82,7 +86,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8 * CG);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&tempty_bar[i], EW * CG);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
@@ -175,9 +179,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp >= GEMM_EPI_WARP0) {
     // ================================ epilogue ====================================
     const int quad = warp & 3;
-    const int half = (warp - GEMM_EPI_WARP0) >> 2;
+    const int half = (warp - GEMM_EPI_WARP0) >> 2;  // which column slice of the tile this warp owns (0 .. EW/4-1)
     const int row_in_tile = quad * 32 + lane;
-    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int COLS_PER_WARP = BN / (EW / 4);
     constexpr int NCHUNK = COLS_PER_WARP / 32;
     int it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
