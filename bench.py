@@ -311,6 +311,8 @@ def main():
         key = c
         kernels[key] = {"ms_per_step": t / args.steps, "launches_per_step": n / args.steps,
                         "tflops": (fl[key] * n_img / (t / 1e3) / 1e12) if key in fl and t > 0 else None}
+    kernels["decoder_parts"] = {c: {"ms_per_step": prof[c][0] / args.steps, "launches_per_step": prof[c][1] / args.steps}
+                                for c in prof if c.startswith("dec_")}
     kernels["decoder"] = {"ms_per_step": dec_ms / args.steps, "launches_per_step": sum(prof[c][1] for c in prof if c.startswith("dec_")) / args.steps,
                           "tflops": fl["decoder"] * n_img / (dec_ms / 1e3) / 1e12 if dec_ms > 0 else None}
     roofline = {

@@ -14,6 +14,9 @@ import json
 d = json.load(open("gpurun_out/bench_${TAG}.json"))
 print("value %.1f img/s  ms/step %.2f  e2e %s  step frac(sustained) %.3f  gemm TF/s %.0f" % (d["value"], d["ms_per_step"], d["e2e"] and round(d["e2e"]["value"],1), d["roofline"]["step"]["frac_of_sustained"], d["roofline"]["achieved"]))
 for k, v in d["roofline"]["kernels"].items():
+    if k == "decoder_parts":
+        for kk, vv in v.items(): print("      %-22s %7.3f ms/step  %5.1f launches" % (kk, vv["ms_per_step"], vv["launches_per_step"]))
+        continue
     print("  %-16s %7.3f ms/step  %5.1f launches  %s TF/s" % (k, v["ms_per_step"], v["launches_per_step"], v["tflops"] and round(v["tflops"])))
 print("clocks", d["clocks"])
 PY
