@@ -148,7 +148,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"SAM {args.model} encoder+decoder, 1024x1024, CPU oracle port of the reference, 1 image/step"},
+        "config": {"workload": f"SAM {args.model} image encoder + mask decoder, 1024x1024, 1 box-shaped prompt per image, "
+                               "random-init weights — the reference's CPU path (oracle port, fp32), bounded sample of 1 image per step",
+                   "images_per_step": 1},
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -298,11 +300,12 @@ def main():
     gemm_launches = sum(prof[c][1] for c in gemm_cats)
     gemm_flops = sum(fl[c] for c in gemm_cats) * n_img
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
-    traffic = None
+    traffic, traffic_detail = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.model == "vit_b" and B == 32:  # the capture is of this exact workload
         with open(tpath) as f:
-            traffic = json.load(f).get("gemm_mlp_lin1_bytes_per_launch")
+            traffic_detail = json.load(f)
+        traffic = traffic_detail.get("gemm_mlp_lin1_bytes_per_launch")
     kernels = {}
     dec_ms = sum(prof[c][0] for c in prof if c.startswith("dec_"))
     for c, (t, n) in prof.items():
@@ -319,6 +322,9 @@ def main():
         "bound": "tensor", "kernel": "gemm_kernel<BN,EPI> (tcgen05): qkv + proj + mlp.lin1 + mlp.lin2 launches",
         "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_sustained"] if achieved else None, "traffic": traffic,
+        "traffic_note": "DRAM read+write bytes of ONE mlp.lin1 launch (largest GEMM of the family; algorithmic 1011 MB) from "
+                        "ncu --set full; per-kernel figures in traffic_detail / profiles/traffic.json",
+        "traffic_detail": traffic_detail,
         "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
         "launches": gemm_launches, "ms_per_launch": gemm_ms / max(gemm_launches, 1),
         "flops_per_launch": gemm_flops / max(gemm_launches, 1),

@@ -79,13 +79,9 @@ struct AttCfg {
 };
 
 ULLSAM_DEVICE float ex2(float x) {
-#ifdef ULLSAM_PROBE_NO_MUFU
-  return fmaf(x, 1e-3f, 1.0f);  // timing probe only: takes the MUFU out of the softmax
-#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-#endif
 }
 
 template <int GRID>
@@ -401,9 +397,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       // ---- exchange with the other half of the row ----
       xch[((j & 1) * 2 + hs) * NROWS + tidq] = mxp;
-#ifndef ULLSAM_PROBE_NO_XCH
       asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-#endif
       const float mx = fmaxf(mxp, xch[((j & 1) * 2 + (hs ^ 1)) * NROWS + tidq]);
 
       // ---- lazy move of the reference point (whole warp: tcgen05.ld/st are collective) ----
