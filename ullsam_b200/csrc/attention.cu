@@ -28,6 +28,11 @@
 // (global: rel_w fp32 in [kw/4][row][4] order for conflict-free 16-byte reads, rel_h as halves) or keeps them
 // in registers (windowed).
 #include "attention.h"
+// 1: global attention with ONE thread per query row (8 softmax warps, row-max bound instead of an exchange);
+// 0: the two-threads-per-row layout that the windowed kernel uses.
+#ifndef ULLSAM_ATT_GLOBAL_ONE_THREAD
+#define ULLSAM_ATT_GLOBAL_ONE_THREAD 1
+#endif
 
 #include "common.cuh"
 #include "gemm.h"
@@ -42,9 +47,10 @@ template <int GRID>
 struct AttCfg {
   static constexpr bool GLOBAL = (GRID == 64);
   static constexpr int QT = GLOBAL ? 2 : 1;               // query tiles per CTA
-  static constexpr int SM_WARPS = QT * 8;                 // softmax warps: 2 threads per query row (one per half tile)
+  static constexpr int SPLIT = (GLOBAL && ULLSAM_ATT_GLOBAL_ONE_THREAD) ? 1 : 2;   // threads per query row
+  static constexpr int SM_WARPS = QT * 4 * SPLIT;         // softmax warps
   static constexpr int CTRL_WARP0 = SM_WARPS;             // first control warp (TMA); +1 = MMA
-  static constexpr int THREADS = (SM_WARPS + (GLOBAL ? 4 : 2)) * 32;   // 640 / 320
+  static constexpr int THREADS = (SM_WARPS + (GLOBAL ? 4 : 2)) * 32;   // 384 (640 with SPLIT 2) / 320
   static constexpr int T = GRID * GRID;
   static constexpr int RPT = GLOBAL ? 2 : 8;              // key-grid rows per tile
   static constexpr int BN = RPT * GRID;                   // keys per tile: 128 / 112
@@ -128,7 +134,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     for (int i = 0; i < NSLOT; ++i) mbar_init(&s_full[i], 1);
     for (int i = 0; i < QT; ++i) {
-      mbar_init(&p_ready[i], 8);
+      mbar_init(&p_ready[i], 4 * A::SPLIT);
       mbar_init(&o_done[2 * i], 1);
       mbar_init(&o_done[2 * i + 1], 1);
     }
@@ -264,8 +270,184 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (n + NSLOT < NITEMS) issue_qk(n + NSLOT);
       }
     }
-  } else if (warp < A::CTRL_WARP0) {
-    // =========================================== softmax warps ==========================================
+  } else if (A::SPLIT == 1 && warp < A::CTRL_WARP0) {
+    // =========================================== softmax warps, one thread per query row =================
+    // (global attention) 4 warps per query tile; thread = row = TMEM lane.  Nothing is exchanged between threads.
+    // The reference point of the exponentials only has to be an UPPER BOUND of the row's biased scores that is not
+    // absurdly loose (softmax is invariant to it; P is bf16 with an 8-bit exponent, O and the row sum are fp32), so
+    // instead of the exact maximum of s*scale + rel_w + rel_h the row uses
+    //     max_k(s) * scale + max_kw(rel_w) + max(rel_h of the tile's two key-grid rows)
+    // which needs one FMNMX3 per two scores in a first pass over the tile; the second pass re-reads the scores from
+    // tensor memory in 32-column pieces (tcgen05.ld bandwidth is plentiful) so that no more than 64 of them are ever
+    // live in registers.  The bound can exceed the true maximum by at most the spread of the bias terms, a few
+    // units in log2 for any real relative-position table.
+    if constexpr (A::SPLIT == 1) {
+      const int qt = warp >> 2;
+      const int quad = warp & 3;
+      const int r = quad * 32 + lane;           // row inside the query tile == TMEM lane
+      const int tidq = qt * 128 + r;            // row inside the CTA
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+      const int tq = qblock * NROWS + tidq;     // query index inside the group
+      const int qh = tq / GRID, qw = tq % GRID;
+      float* relw_s = reinterpret_cast<float*>(smem + A::OFF_RELW);
+      __half* relh_s = reinterpret_cast<__half*>(smem + A::OFF_RELH);
+
+      // ---- prologue: scatter this row's 64 rel_w and 64 rel_h values (log2 units), remember max(rel_w) ----
+      mbar_wait(pro_mma_done, 0);
+      tc_fence_after();
+      float wmax = -INFINITY;
+#pragma unroll
+      for (int tbl = 0; tbl < 2; ++tbl) {
+        const uint32_t col_t = (tbl ? 256 : 0) + qt * 128;
+        const int q0 = tbl ? qh : qw;
+#pragma unroll
+        for (int c = 0; c < A::NREL / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + col_t + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kk = q0 + (GRID - 1) - (c * 32 + i);
+            if (kk >= 0 && kk < GRID) {
+              const float val = __uint_as_float(v[i]) * kLog2e;
+              if (tbl) {
+                relh_s[kk * NROWS + tidq] = __float2half_rn(val);
+              } else {
+                relw_s[((kk >> 2) * NROWS + tidq) * 4 + (kk & 3)] = val;
+                wmax = fmaxf(wmax, val);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pro_consumed);  // the prologue's TMEM columns may now be overwritten
+
+      // ---- main loop ----
+      const float cs = 0.125f * kLog2e;  // head_dim 64: scale = 1/8, folded with log2(e)
+      float m_used = -INFINITY;          // reference point of the exponentials (log2 units)
+      float l0 = 0.f, l1 = 0.f;          // row sum (two accumulation chains)
+      const uint32_t o_addr = lane_addr + A::COL_O + qt * 64;
+      const float* wrow = relw_s + tidq * 4;
+
+#pragma unroll 1
+      for (int j = 0; j < NT; ++j) {
+        const int n = j * QT + qt;
+        const uint32_t s_addr = lane_addr + (n % NSLOT) * 128;
+        mbar_wait(&s_full[n % NSLOT], (n / NSLOT) & 1);
+        tc_fence_after();
+
+        // ---- pass A: maximum of the raw scores of the row ----
+        uint32_t b0[32], b1[32];
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        auto fold = [&](const uint32_t (&b)[32]) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            mx0 = fmax3(mx0, __uint_as_float(b[i]), __uint_as_float(b[i + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(b[i + 2]), __uint_as_float(b[i + 3]));
+            mx2 = fmax3(mx2, __uint_as_float(b[i + 4]), __uint_as_float(b[i + 5]));
+            mx3 = fmax3(mx3, __uint_as_float(b[i + 6]), __uint_as_float(b[i + 7]));
+          }
+        };
+        tmem_ld32(s_addr, b0);
+        tmem_ld32(s_addr + 32, b1);
+        tmem_wait_ld();
+        fold(b0);
+        tmem_ld32(s_addr + 64, b0);
+        fold(b1);
+        tmem_ld32(s_addr + 96, b1);
+        tmem_wait_ld();
+        fold(b0);
+        tmem_ld32(s_addr, b0);          // first piece of pass B
+        fold(b1);
+        const float rh0 = __half2float(relh_s[(2 * j) * NROWS + tidq]);
+        const float rh1 = __half2float(relh_s[(2 * j + 1) * NROWS + tidq]);
+        const float mx = fmaf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), cs, wmax + fmaxf(rh0, rh1));
+
+        // ---- lazy move of the reference point (whole warp: tcgen05.ld/st are collective) ----
+        // PV(j) commits to o_done[qt][j & 1].  An mbarrier parity wait may never lag two phases behind, so every
+        // phase of both barriers is observed in order: routinely two tiles late (end of this loop body, where it
+        // never stalls), and exactly on time only when O really has to be touched here.
+        const bool need = mx > m_used + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? ex2(m_used - mx) : 1.0f;  // first tile: 2^-inf = 0, and l, O are empty
+          l0 *= alpha;
+          l1 *= alpha;
+          if (j > 0) {
+            mbar_wait(&o_done[qt * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);  // PV(j-1) retired: O is quiescent
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              tmem_ld32(o_addr + h * 32, b1);
+              tmem_wait_ld();   // (also completes the pass-B prefetch)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) b1[i] = __float_as_uint(__uint_as_float(b1[i]) * alpha);
+              tmem_st32(o_addr + h * 32, b1);
+            }
+          }
+          if (need) m_used = mx;
+        }
+
+        // ---- pass B: P = 2^(s*scale + rel_h + rel_w - m), 32 keys at a time, double-buffered TMEM reads ----
+        const float c0 = rh0 - m_used, c1 = rh1 - m_used;
+        auto piece = [&](const uint32_t (&b)[32], int c) {   // keys [32c, 32c+32) of the tile
+          const float cc = (c < 2) ? c0 : c1;               // key-grid row 2j + c/2, key-grid columns (c&1)*32 ..
+          uint32_t pk[16];
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const float4 w = *reinterpret_cast<const float4*>(wrow + ((c & 1) * 8 + k4) * NROWS * 4);
+            const float p0 = ex2(fmaf(__uint_as_float(b[4 * k4]), cs, cc) + w.x);
+            const float p1 = ex2(fmaf(__uint_as_float(b[4 * k4 + 1]), cs, cc) + w.y);
+            const float p2 = ex2(fmaf(__uint_as_float(b[4 * k4 + 2]), cs, cc) + w.z);
+            const float p3 = ex2(fmaf(__uint_as_float(b[4 * k4 + 3]), cs, cc) + w.w);
+            l0 += p0 + p2;
+            l1 += p1 + p3;
+            pk[2 * k4] = pack_bf16(p0, p1);
+            pk[2 * k4 + 1] = pack_bf16(p2, p3);
+          }
+          tmem_st16(s_addr + c * 16, pk);  // overwrites score columns [16c, 16c+16): already consumed
+        };
+        tmem_wait_ld();
+        tmem_ld32(s_addr + 32, b1);
+        piece(b0, 0);
+        tmem_wait_ld();
+        tmem_ld32(s_addr + 64, b0);
+        piece(b1, 1);
+        tmem_wait_ld();
+        tmem_ld32(s_addr + 96, b1);
+        piece(b0, 2);
+        tmem_wait_ld();
+        piece(b1, 3);
+        tmem_wait_st();
+        if (j > 1) mbar_wait(&o_done[qt * 2 + (j & 1)], ((j - 2) >> 1) & 1);  // PV(j-2): long retired
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[qt]);
+      }
+
+      // ---- epilogue: O / l -> out ----
+      mbar_wait(&o_done[qt * 2 + ((NT - 1) & 1)], ((NT - 1) >> 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / (l0 + l1);
+      const long out_row = static_cast<long>(gh / heads) * A::T + tq;
+      const int head = gh % heads;
+      uint4* dst = reinterpret_cast<uint4*>(out + (out_row * heads + head) * 64);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t o[32];
+        tmem_ld32(o_addr + h * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          dst[h * 4 + u] = make_uint4(pack_bf16(__uint_as_float(o[8 * u]) * inv_l, __uint_as_float(o[8 * u + 1]) * inv_l),
+                                      pack_bf16(__uint_as_float(o[8 * u + 2]) * inv_l, __uint_as_float(o[8 * u + 3]) * inv_l),
+                                      pack_bf16(__uint_as_float(o[8 * u + 4]) * inv_l, __uint_as_float(o[8 * u + 5]) * inv_l),
+                                      pack_bf16(__uint_as_float(o[8 * u + 6]) * inv_l, __uint_as_float(o[8 * u + 7]) * inv_l));
+      }
+    }
+  } else if (A::SPLIT == 2 && warp < A::CTRL_WARP0) {
+    // =========================================== softmax warps, two threads per query row ================
     // Two threads per query row: thread (row, hs) owns columns [hs*HALF, hs*HALF + HALF) of every S tile, i.e. one
     // key-grid row per tile for the global grid.  The pair lives in two warps of the same TMEM lane quadrant and
     // exchanges its partial row max (every tile) and row sum (once, at the end) through shared memory.
