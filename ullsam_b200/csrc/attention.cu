@@ -30,6 +30,15 @@
 #include "attention.h"
 // 1: global attention with ONE thread per query row (8 softmax warps, row-max bound instead of an exchange);
 // 0: the two-threads-per-row layout that the windowed kernel uses.
+// 1: (debug builds only, tools/build_variant.sh) print a per-phase cycle breakdown of two softmax warps of CTA (0,0)
+#ifndef ULLSAM_ATT_TIMELINE
+#define ULLSAM_ATT_TIMELINE 0
+#endif
+#if ULLSAM_ATT_TIMELINE
+#define TL_STAMP(i) do { const long long t_ = clock64(); tl[i] += t_ - tl_last; tl_last = t_; } while (0)
+#else
+#define TL_STAMP(i) do { } while (0)
+#endif
 #ifndef ULLSAM_ATT_GLOBAL_ONE_THREAD
 #define ULLSAM_ATT_GLOBAL_ONE_THREAD 1
 #endif
@@ -84,11 +93,46 @@ struct AttCfg {
   static constexpr int OFF_RELTAB_H = GLOBAL ? OFF_V + (VSTAGES - 1) * KVSLOT : OFF_RELTAB_W + 4096;
 };
 
+// size-overloaded TMEM accessors (the piece size of the softmax is a compile-time knob)
+ULLSAM_DEVICE void tmem_ld_n(uint32_t a, uint32_t (&v)[16]) { tmem_ld16(a, v); }
+ULLSAM_DEVICE void tmem_ld_n(uint32_t a, uint32_t (&v)[32]) { tmem_ld32(a, v); }
+ULLSAM_DEVICE void tmem_st_n(uint32_t a, const uint32_t (&v)[8]) { tmem_st8(a, v); }
+ULLSAM_DEVICE void tmem_st_n(uint32_t a, const uint32_t (&v)[16]) { tmem_st16(a, v); }
+
 ULLSAM_DEVICE float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial, relative error 7.5e-5, far below the
+// bf16 rounding of P): the MUFU unit issues one warp-wide ex2 per 8 cycles per sub-partition and is the bottleneck of
+// the softmax, so a fraction of the exponentials is computed here instead (the FlashAttention-4 trick).
+ULLSAM_DEVICE float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);                         // keep the result a normal number
+  const float xr = x + 12582912.0f;              // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (xr - 12582912.0f);        // in [-0.5, 0.5]
+  float p = fmaf(f, 0.0551716648f, 0.2426111251f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));   // p * 2^round(x)
+}
+// bit e set: element e of every group of 8 consecutive keys uses ex2_poly instead of MUFU.EX2
+// Register re-allocation between warpgroups (global kernel, one thread per row): the kernel is launched with 168
+// registers per thread (384 threads); the control warpgroup gives most of its share back and the two softmax
+// warpgroups grow, so each softmax thread can keep its 64 rel_w bias values in registers for the whole kernel.
+#ifndef ULLSAM_ATT_REGS_SOFTMAX
+#define ULLSAM_ATT_REGS_SOFTMAX 224
+#endif
+#ifndef ULLSAM_ATT_REGS_CTRL
+#define ULLSAM_ATT_REGS_CTRL 56
+#endif
+#ifndef ULLSAM_ATT_PIECE
+#define ULLSAM_ATT_PIECE 16
+#endif
+#ifndef ULLSAM_ATT_POLY_MASK
+#define ULLSAM_ATT_POLY_MASK 0x00
+#endif
 
 template <int GRID>
 __global__ void __launch_bounds__(AttCfg<GRID>::THREADS, AttCfg<GRID>::GLOBAL ? 1 : 2)
@@ -148,6 +192,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // Role dispatch.  Global kernel with one thread per row: warps 0..7 are the two softmax warpgroups, warps 8..11 the
+  // control warpgroup; setmaxnreg is warpgroup-uniform and is the first thing each side executes.
+  if (warp >= A::CTRL_WARP0) {
+  if constexpr (A::SPLIT == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ULLSAM_ATT_REGS_CTRL));
 
   if (warp == A::CTRL_WARP0) {
     // =========================================== TMA producers ==========================================
@@ -216,26 +265,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         __syncwarp();
       };
-      auto issue_pv = [&](int n) {  // O[qt] (+)= P(n) V(j), P read from the first BN/2 columns of slot n % NSLOT
-        const int j = n / QT, qt = n % QT, stage = j % VS;
-        if (qt == 0) {
-          mbar_wait(&v_full[stage], (j / VS) & 1);
-          tc_fence_after();
-        }
-        const uint64_t dv = make_smem_desc_sw128(sv + stage * A::KVSLOT, 16, 1024);
-        if (leader) {
-#pragma unroll
-          for (int s = 0; s < BN / 16; ++s) {
-            // 16 keys per step: 8 TMEM columns of packed bf16 pairs; 16 V rows x 128 B = 2048 B of shared memory
-            umma_ts(tmem_base + A::COL_O + qt * 64, tmem_base + (n % NSLOT) * 128 + s * 8, dv + s * 128, idesc_pv,
-                    (j | s) != 0);
-          }
-          umma_commit(&o_done[qt * 2 + (j & 1)]);
-          if (qt == QT - 1) umma_commit(&v_empty[stage]);
-        }
-        __syncwarp();
-      };
-
       // ---- prologue: Tw[qt] = Q[qt] Rw^T, Th[qt] = Q[qt] Rh^T ----
       mbar_wait(q_full, 0);
       tc_fence_after();
@@ -262,15 +291,66 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(pro_consumed, 0);
       tc_fence_after();
       for (int n = 0; n < NSLOT && n < NITEMS; ++n) issue_qk(n);
+      // Steady state, item n: O[qt] += P(n) V(j), then S(n + NSLOT) into the slot P(n) vacates (tcgen05 ops of one
+      // thread execute in issue order).  The hand-over P(n) -> S(n + NSLOT) sits on the critical path of the softmax
+      // warps, so everything that does not depend on P(n) — the operand barriers and all descriptor arithmetic —
+      // is done BEFORE waiting for it; after the wait there is only the fence and the MMA issue itself.
+#if ULLSAM_ATT_TIMELINE
+      long long mma_tl[3] = {0, 0, 0};
+      long long mma_last = clock64();
+#endif
       for (int n = 0; n < NITEMS; ++n) {
-        mbar_wait(&p_ready[n % QT], (n / QT) & 1);  // P(n) is in its slot
+        const int j = n / QT, qt = n % QT, vstage = j % VS;
+        const int n2 = n + NSLOT, j2 = n2 / QT, qt2 = n2 % QT, kstage = j2 % KS;
+        const bool has_qk = n2 < NITEMS;
+        if (qt == 0) mbar_wait(&v_full[vstage], (j / VS) & 1);
+        if (has_qk && qt2 == 0) mbar_wait(&k_full[kstage], (j2 / KS) & 1);
+        const uint64_t dv = make_smem_desc_sw128(sv + vstage * A::KVSLOT, 16, 1024);
+        const uint64_t dq = make_smem_desc_sw128(sq + qt2 * A::QBYTES, 16, 1024);
+        const uint64_t dk = make_smem_desc_sw128(sk + kstage * A::KVSLOT, 16, 1024);
+        const uint32_t t_slot = tmem_base + (n % NSLOT) * 128;   // P(n) now, S(n2) next
+        const uint32_t t_o = tmem_base + A::COL_O + qt * 64;
+        uint64_t* bar_o = &o_done[qt * 2 + (j & 1)];
+        uint64_t* bar_s = &s_full[n % NSLOT];
+#if ULLSAM_ATT_TIMELINE
+        const long long mt0 = clock64();
+#endif
+        mbar_wait(&p_ready[qt], j & 1);  // P(n) is in its slot
         tc_fence_after();
-        issue_pv(n);
-        // tcgen05 ops of one thread execute in issue order: the next S may overwrite this slot once PV(n) has read it
-        if (n + NSLOT < NITEMS) issue_qk(n + NSLOT);
+#if ULLSAM_ATT_TIMELINE
+        const long long mt1 = clock64();
+#endif
+        if (leader) {
+#pragma unroll
+          for (int s2 = 0; s2 < BN / 16; ++s2)
+            umma_ts(t_o, t_slot + s2 * 8, dv + s2 * 128, idesc_pv, (j | s2) != 0);
+          umma_commit(bar_o);
+          if (qt == QT - 1) umma_commit(&v_empty[vstage]);
+          if (has_qk) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss(t_slot, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+            umma_commit(bar_s);
+            if (qt2 == QT - 1) umma_commit(&k_empty[kstage]);
+          }
+        }
+        __syncwarp();
+#if ULLSAM_ATT_TIMELINE
+        mma_tl[0] += mt0 - mma_last;      // operand waits + descriptor prep
+        mma_tl[1] += mt1 - mt0;           // waiting for P(n)
+        mma_last = clock64();
+        mma_tl[2] += mma_last - mt1;      // issuing the MMAs
+#endif
       }
+#if ULLSAM_ATT_TIMELINE
+      if (blockIdx.x == 0 && blockIdx.y == 0 && leader)
+        printf("mma warp per item: prep+operand waits %lld | wait P %lld | issue %lld\n", mma_tl[0] / NITEMS, mma_tl[1] / NITEMS,
+               mma_tl[2] / NITEMS);
+#endif
     }
-  } else if (A::SPLIT == 1 && warp < A::CTRL_WARP0) {
+  }
+  }  // control warpgroup
+  else if (A::SPLIT == 1) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ULLSAM_ATT_REGS_SOFTMAX));
     // =========================================== softmax warps, one thread per query row =================
     // (global attention) 4 warps per query tile; thread = row = TMEM lane.  Nothing is exchanged between threads.
     // The reference point of the exponentials only has to be an UPPER BOUND of the row's biased scores that is not
@@ -323,20 +403,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pro_consumed);  // the prologue's TMEM columns may now be overwritten
+      // the row's 64 rel_w values stay in registers for the whole kernel (they only depend on (q, kw))
+      float wreg[64];
+#pragma unroll
+      for (int k4 = 0; k4 < 16; ++k4) {
+        const float4 w = *reinterpret_cast<const float4*>(relw_s + (k4 * NROWS + tidq) * 4);
+        wreg[4 * k4] = w.x; wreg[4 * k4 + 1] = w.y; wreg[4 * k4 + 2] = w.z; wreg[4 * k4 + 3] = w.w;
+      }
 
       // ---- main loop ----
       const float cs = 0.125f * kLog2e;  // head_dim 64: scale = 1/8, folded with log2(e)
       float m_used = -INFINITY;          // reference point of the exponentials (log2 units)
       float l0 = 0.f, l1 = 0.f;          // row sum (two accumulation chains)
       const uint32_t o_addr = lane_addr + A::COL_O + qt * 64;
-      const float* wrow = relw_s + tidq * 4;
 
+#if ULLSAM_ATT_TIMELINE
+      long long tl[7] = {0, 0, 0, 0, 0, 0, 0};
+      long long tl_last = clock64();
+      const long long tl_begin = tl_last;
+#endif
 #pragma unroll 1
       for (int j = 0; j < NT; ++j) {
         const int n = j * QT + qt;
         const uint32_t s_addr = lane_addr + (n % NSLOT) * 128;
+        TL_STAMP(5);
         mbar_wait(&s_full[n % NSLOT], (n / NSLOT) & 1);
         tc_fence_after();
+        TL_STAMP(0);
 
         // ---- pass A: maximum of the raw scores of the row ----
         uint32_t b0[32], b1[32];
@@ -355,11 +448,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_wait_ld();
         fold(b0);
         tmem_ld32(s_addr + 64, b0);
+        pin32(b1);                      // (see pin32: keeps the prefetch ahead of the arithmetic)
         fold(b1);
         tmem_ld32(s_addr + 96, b1);
         tmem_wait_ld();
         fold(b0);
-        tmem_ld32(s_addr, b0);          // first piece of pass B
         fold(b1);
         const float rh0 = __half2float(relh_s[(2 * j) * NROWS + tidq]);
         const float rh1 = __half2float(relh_s[(2 * j + 1) * NROWS + tidq]);
@@ -370,6 +463,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // phase of both barriers is observed in order: routinely two tiles late (end of this loop body, where it
         // never stalls), and exactly on time only when O really has to be touched here.
         const bool need = mx > m_used + 8.0f;
+        TL_STAMP(1);
         if (__any_sync(0xffffffffu, need)) {
           const float alpha = need ? ex2(m_used - mx) : 1.0f;  // first tile: 2^-inf = 0, and l, O are empty
           l0 *= alpha;
@@ -380,7 +474,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               tmem_ld32(o_addr + h * 32, b1);
-              tmem_wait_ld();   // (also completes the pass-B prefetch)
+              tmem_wait_ld();
 #pragma unroll
               for (int i = 0; i < 32; ++i) b1[i] = __float_as_uint(__uint_as_float(b1[i]) * alpha);
               tmem_st32(o_addr + h * 32, b1);
@@ -389,42 +483,63 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (need) m_used = mx;
         }
 
-        // ---- pass B: P = 2^(s*scale + rel_h + rel_w - m), 32 keys at a time, double-buffered TMEM reads ----
+        TL_STAMP(2);
+        // ---- pass B: P = 2^(s*scale + rel_h + rel_w - m), PIECE keys at a time, double-buffered TMEM reads ----
+        // (small pieces keep the register pressure low enough for ptxas to issue the next tcgen05.ld early)
         const float c0 = rh0 - m_used, c1 = rh1 - m_used;
-        auto piece = [&](const uint32_t (&b)[32], int c) {   // keys [32c, 32c+32) of the tile
-          const float cc = (c < 2) ? c0 : c1;               // key-grid row 2j + c/2, key-grid columns (c&1)*32 ..
-          uint32_t pk[16];
+        constexpr int PIECE = ULLSAM_ATT_PIECE, NP = 128 / PIECE;
+        uint32_t pb[2][PIECE];
+        auto piece = [&](const uint32_t (&b)[PIECE], int c) {   // keys [PIECE*c, PIECE*c + PIECE) of the tile
+          const float cc = (c < NP / 2) ? c0 : c1;               // key-grid row 2j + (c >= NP/2)
+          const int kw0 = (c % (NP / 2)) * PIECE;                // first key-grid column of the piece
+          uint32_t pk[PIECE / 2];
 #pragma unroll
-          for (int k4 = 0; k4 < 8; ++k4) {
-            const float4 w = *reinterpret_cast<const float4*>(wrow + ((c & 1) * 8 + k4) * NROWS * 4);
-            const float p0 = ex2(fmaf(__uint_as_float(b[4 * k4]), cs, cc) + w.x);
-            const float p1 = ex2(fmaf(__uint_as_float(b[4 * k4 + 1]), cs, cc) + w.y);
-            const float p2 = ex2(fmaf(__uint_as_float(b[4 * k4 + 2]), cs, cc) + w.z);
-            const float p3 = ex2(fmaf(__uint_as_float(b[4 * k4 + 3]), cs, cc) + w.w);
+          for (int k4 = 0; k4 < PIECE / 4; ++k4) {
+            const int kw = kw0 + 4 * k4;
+            const float x0 = fmaf(__uint_as_float(b[4 * k4]), cs, cc) + wreg[kw];
+            const float x1 = fmaf(__uint_as_float(b[4 * k4 + 1]), cs, cc) + wreg[kw + 1];
+            const float x2 = fmaf(__uint_as_float(b[4 * k4 + 2]), cs, cc) + wreg[kw + 2];
+            const float x3 = fmaf(__uint_as_float(b[4 * k4 + 3]), cs, cc) + wreg[kw + 3];
+            constexpr int M = ULLSAM_ATT_POLY_MASK;
+            const int e = (k4 & 1) * 4;
+            const float p0 = ((M >> (e + 0)) & 1) ? ex2_poly(x0) : ex2(x0);
+            const float p1 = ((M >> (e + 1)) & 1) ? ex2_poly(x1) : ex2(x1);
+            const float p2 = ((M >> (e + 2)) & 1) ? ex2_poly(x2) : ex2(x2);
+            const float p3 = ((M >> (e + 3)) & 1) ? ex2_poly(x3) : ex2(x3);
             l0 += p0 + p2;
             l1 += p1 + p3;
             pk[2 * k4] = pack_bf16(p0, p1);
             pk[2 * k4 + 1] = pack_bf16(p2, p3);
           }
-          tmem_st16(s_addr + c * 16, pk);  // overwrites score columns [16c, 16c+16): already consumed
+          tmem_st_n(s_addr + c * (PIECE / 2), pk);   // overwrites score columns already consumed
         };
-        tmem_wait_ld();
-        tmem_ld32(s_addr + 32, b1);
-        piece(b0, 0);
-        tmem_wait_ld();
-        tmem_ld32(s_addr + 64, b0);
-        piece(b1, 1);
-        tmem_wait_ld();
-        tmem_ld32(s_addr + 96, b1);
-        piece(b0, 2);
-        tmem_wait_ld();
-        piece(b1, 3);
+        auto load_piece = [&](uint32_t (&b)[PIECE], int c) {
+          tmem_ld_n(s_addr + c * PIECE, b);
+        };
+        load_piece(pb[0], 0);
+#pragma unroll
+        for (int c = 0; c < NP; ++c) {
+          tmem_wait_ld();
+          if (c + 1 < NP) load_piece(pb[(c + 1) & 1], c + 1);
+          piece(pb[c & 1], c);
+        }
+        TL_STAMP(3);
         tmem_wait_st();
         if (j > 1) mbar_wait(&o_done[qt * 2 + (j & 1)], ((j - 2) >> 1) & 1);  // PV(j-2): long retired
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[qt]);
+        TL_STAMP(4);
+#if ULLSAM_ATT_TIMELINE == 2
+        mbar_wait(&o_done[qt * 2 + (j & 1)], (j >> 1) & 1);  // probe: P(n) handed over -> PV(n) retired
+        TL_STAMP(6);
+#endif
       }
+#if ULLSAM_ATT_TIMELINE
+      if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && quad == 0)
+        printf("qt %d: per tile: wait S %lld | pass A %lld | rescale %lld | pass B %lld | tail %lld | loop %lld | PV probe %lld | total/tile %lld\n",
+               qt, tl[0] / NT, tl[1] / NT, tl[2] / NT, tl[3] / NT, tl[4] / NT, tl[5] / NT, tl[6] / NT, (clock64() - tl_begin) / NT);
+#endif
 
       // ---- epilogue: O / l -> out ----
       mbar_wait(&o_done[qt * 2 + ((NT - 1) & 1)], ((NT - 1) >> 1) & 1);
@@ -446,7 +561,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                                       pack_bf16(__uint_as_float(o[8 * u + 6]) * inv_l, __uint_as_float(o[8 * u + 7]) * inv_l));
       }
     }
-  } else if (A::SPLIT == 2 && warp < A::CTRL_WARP0) {
+  } else if (A::SPLIT == 2) {
     // =========================================== softmax warps, two threads per query row ================
     // Two threads per query row: thread (row, hs) owns columns [hs*HALF, hs*HALF + HALF) of every S tile, i.e. one
     // key-grid row per tile for the global grid.  The pair lives in two warps of the same TMEM lane quadrant and

@@ -68,6 +68,9 @@ ULLSAM_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
 
 // try_wait with a suspend-time hint: the waiting thread sleeps (NANOSLEEP.SYNCS) instead of re-polling, which
 // leaves the issue slots of its SM sub-partition to the compute warps (measured: GEMM lin2 1.31 -> 1.44 PF/s).
+#ifndef ULLSAM_TRYWAIT_HINT
+#define ULLSAM_TRYWAIT_HINT 20000u
+#endif
 ULLSAM_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
 #ifndef ULLSAM_TRYWAIT_NO_HINT
@@ -78,7 +81,7 @@ ULLSAM_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "selp.b32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ULLSAM_TRYWAIT_HINT)
       : "memory");
 #else
   asm volatile(
@@ -198,6 +201,18 @@ ULLSAM_DEVICE void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
+}
+
+// Scheduling fence for register values: an empty volatile asm that "rewrites" v, so every later use of v is ordered
+// after the volatile asms that precede it (e.g. the tcgen05.ld that prefetches the NEXT buffer).  Without it ptxas
+// hoists the arithmetic on the current buffer above the prefetch and the TMEM latency is exposed again.
+ULLSAM_DEVICE void pin32(uint32_t (&v)[32]) {
+  asm volatile(""
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]),
+                 "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),
+                 "+r"(v[30]), "+r"(v[31]));
 }
 
 ULLSAM_DEVICE void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
