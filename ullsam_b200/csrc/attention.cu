@@ -431,37 +431,43 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         TL_STAMP(0);
 
-        // ---- pass A: maximum of the raw scores of the row ----
-        uint32_t b0[32], b1[32];
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-        auto fold = [&](const uint32_t (&b)[32]) {
+        // ---- pass A: maximum of the raw scores of the row (all four tcgen05.ld in flight at once) ----
+        constexpr int PIECE = ULLSAM_ATT_PIECE, NP = 128 / PIECE;
+        uint32_t pb[2][PIECE];
+        float mxs;
+        {
+          uint32_t a0[32], a1[32], a2[32], a3[32];
+          tmem_ld32(s_addr, a0);
+          tmem_ld32(s_addr + 32, a1);
+          tmem_ld32(s_addr + 64, a2);
+          tmem_ld32(s_addr + 96, a3);
+          tmem_wait_ld();
+          tmem_ld_n(s_addr, pb[0]);   // first piece of pass B, in flight while the maximum is folded
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          float m4 = -INFINITY, m5 = -INFINITY, m6 = -INFINITY, m7 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            mx0 = fmax3(mx0, __uint_as_float(b[i]), __uint_as_float(b[i + 1]));
-            mx1 = fmax3(mx1, __uint_as_float(b[i + 2]), __uint_as_float(b[i + 3]));
-            mx2 = fmax3(mx2, __uint_as_float(b[i + 4]), __uint_as_float(b[i + 5]));
-            mx3 = fmax3(mx3, __uint_as_float(b[i + 6]), __uint_as_float(b[i + 7]));
+          for (int i = 0; i < 32; i += 4) {
+            m0 = fmax3(m0, __uint_as_float(a0[i]), __uint_as_float(a0[i + 1]));
+            m1 = fmax3(m1, __uint_as_float(a0[i + 2]), __uint_as_float(a0[i + 3]));
+            m2 = fmax3(m2, __uint_as_float(a1[i]), __uint_as_float(a1[i + 1]));
+            m3 = fmax3(m3, __uint_as_float(a1[i + 2]), __uint_as_float(a1[i + 3]));
+            m4 = fmax3(m4, __uint_as_float(a2[i]), __uint_as_float(a2[i + 1]));
+            m5 = fmax3(m5, __uint_as_float(a2[i + 2]), __uint_as_float(a2[i + 3]));
+            m6 = fmax3(m6, __uint_as_float(a3[i]), __uint_as_float(a3[i + 1]));
+            m7 = fmax3(m7, __uint_as_float(a3[i + 2]), __uint_as_float(a3[i + 3]));
           }
-        };
-        tmem_ld32(s_addr, b0);
-        tmem_ld32(s_addr + 32, b1);
-        tmem_wait_ld();
-        fold(b0);
-        tmem_ld32(s_addr + 64, b0);
-        pin32(b1);                      // (see pin32: keeps the prefetch ahead of the arithmetic)
-        fold(b1);
-        tmem_ld32(s_addr + 96, b1);
-        tmem_wait_ld();
-        fold(b0);
-        fold(b1);
+          mxs = fmaxf(fmaxf(fmax3(m0, m1, m2), fmax3(m3, m4, m5)), fmaxf(m6, m7));
+        }
         const float rh0 = __half2float(relh_s[(2 * j) * NROWS + tidq]);
         const float rh1 = __half2float(relh_s[(2 * j + 1) * NROWS + tidq]);
-        const float mx = fmaf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), cs, wmax + fmaxf(rh0, rh1));
+        const float mx = fmaf(mxs, cs, wmax + fmaxf(rh0, rh1));
 
         // ---- lazy move of the reference point (whole warp: tcgen05.ld/st are collective) ----
-        // PV(j) commits to o_done[qt][j & 1].  An mbarrier parity wait may never lag two phases behind, so every
-        // phase of both barriers is observed in order: routinely two tiles late (end of this loop body, where it
-        // never stalls), and exactly on time only when O really has to be touched here.
+        // PV(j) commits to o_done[qt][j & 1]; O is only touched here, after waiting for PV(j-1).  That parity wait is
+        // unambiguous without observing the earlier phases: S(n) was issued after PV(n-3), tcgen05 ops of one thread
+        // complete in order, so having seen s_full for this tile means PV(j-2) and PV(j-3) of this query tile have
+        // retired (the barrier cannot be a phase behind), and PV(j+1) cannot be issued before this warp hands P(j+1)
+        // over (it cannot be a phase ahead).
         const bool need = mx > m_used + 8.0f;
         TL_STAMP(1);
         if (__any_sync(0xffffffffu, need)) {
@@ -473,6 +479,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tc_fence_after();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
+              uint32_t b1[32];
               tmem_ld32(o_addr + h * 32, b1);
               tmem_wait_ld();
 #pragma unroll
@@ -487,8 +494,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // ---- pass B: P = 2^(s*scale + rel_h + rel_w - m), PIECE keys at a time, double-buffered TMEM reads ----
         // (small pieces keep the register pressure low enough for ptxas to issue the next tcgen05.ld early)
         const float c0 = rh0 - m_used, c1 = rh1 - m_used;
-        constexpr int PIECE = ULLSAM_ATT_PIECE, NP = 128 / PIECE;
-        uint32_t pb[2][PIECE];
         auto piece = [&](const uint32_t (&b)[PIECE], int c) {   // keys [PIECE*c, PIECE*c + PIECE) of the tile
           const float cc = (c < NP / 2) ? c0 : c1;               // key-grid row 2j + (c >= NP/2)
           const int kw0 = (c % (NP / 2)) * PIECE;                // first key-grid column of the piece
@@ -516,7 +521,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         auto load_piece = [&](uint32_t (&b)[PIECE], int c) {
           tmem_ld_n(s_addr + c * PIECE, b);
         };
-        load_piece(pb[0], 0);
 #pragma unroll
         for (int c = 0; c < NP; ++c) {
           tmem_wait_ld();
@@ -525,13 +529,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         TL_STAMP(3);
         tmem_wait_st();
-        if (j > 1) mbar_wait(&o_done[qt * 2 + (j & 1)], ((j - 2) >> 1) & 1);  // PV(j-2): long retired
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[qt]);
         TL_STAMP(4);
 #if ULLSAM_ATT_TIMELINE == 2
         mbar_wait(&o_done[qt * 2 + (j & 1)], (j >> 1) & 1);  // probe: P(n) handed over -> PV(n) retired
+        TL_STAMP(6);
+#elif ULLSAM_ATT_TIMELINE == 3
+        if (n + NSLOT < NITEMS) mbar_wait(&s_full[n % NSLOT], ((n + NSLOT) / NSLOT) & 1);  // probe: -> S(n + NSLOT) ready
         TL_STAMP(6);
 #endif
       }
