@@ -145,7 +145,9 @@ const char* ullsam_profile_category_name(int i);
 
 /* tcgen05 GEMM: C = A[M,K] x W[N,K]^T with a fused epilogue.  Mirrors ullsam::GemmParams. */
 typedef struct {
-  int32_t epi;  /* 0 bf16 | 1 +residual fp32 | 2 qkv split | 3 +pos fp32 | 4 LN2d bf16 | 5 LN2d NCHW | 6 fp32 */
+  int32_t epi;  /* 0 bf16 | 1 +residual fp32 | 2 qkv split | 3 +pos fp32 | 4 LN2d bf16 | 5 LN2d NCHW | 6 fp32 |
+                 * 11 +residual fp32 AND the following nn.LayerNorm -> out2 bf16 (Block.norm2 / next Block.norm1,
+                 *    image_encoder.py:166-182), optionally window-partitioned (image_encoder.py:243-264) */
   int32_t M, N, K;
   int32_t a_conv3, conv_c;
   const void* A;     /* bf16 */
@@ -165,6 +167,8 @@ typedef struct {
   const float* ln_b;
   float ln_eps;
   int32_t hw;
+  void* out2;           /* epi 11: bf16 LayerNorm(out) [M, N] (token order) or [M/4096*25*196, N] (window order) */
+  int32_t ln_partition; /* epi 11: 1 = window order (pad rows are not written) */
 } ullsam_gemm_desc;
 int ullsam_op_gemm(const ullsam_gemm_desc* d, void* stream);
 

@@ -58,6 +58,35 @@ def test_gemm_residual_inplace():
     _close(x, ref, 1e-4, "residual")
 
 
+@pytest.mark.parametrize("partition", [False, True])
+@pytest.mark.parametrize("K", [768, 3072])
+def test_gemm_residual_with_fused_layernorm(K, partition):
+    """EPI_RES_LN: x += A W^T + b in place AND bf16 LayerNorm(x) of the updated rows (Block.norm2 / next norm1,
+    image_encoder.py:166-182), in token order or in window_partition order (image_encoder.py:243-264)."""
+    from ullsam_b200 import _lib, ops
+
+    B, dim = 3, 768
+    M = B * 4096   # includes a tail: 12288 rows = 48 row blocks of 256, dealt M-major to the CTA pairs
+    a, w, b = _mk(M, dim, K, 21)
+    res = torch.randn(M, dim, device="cuda") * 3.0 + 0.5   # non-zero mean, larger scale than the GEMM term
+    gamma = 1.0 + 0.1 * torch.randn(dim, device="cuda")
+    beta = 0.1 * torch.randn(dim, device="cuda")
+    x_ref = _ref(a, w, b) + res
+    ln_ref = torch.nn.functional.layer_norm(x_ref, (dim,), gamma, beta, 1e-6)
+    x = res.clone()
+    rows = B * 25 * 196 if partition else M
+    xn = torch.full((rows, dim), 7.0, dtype=torch.bfloat16, device="cuda")   # sentinel: pad rows must stay untouched
+    ops.gemm(a, w, b, epi=_lib.EPI_RES_LN, out=x, residual=x, ln_w=gamma, ln_b=beta, ln_eps=1e-6, out2=xn,
+             ln_partition=partition)
+    _close(x, x_ref, 1e-4, f"res+ln K={K}: residual stream")
+    if partition:
+        # reference window partition (pad 64 -> 70, 5x5 windows of 14x14), zero pad rows replaced by the sentinel
+        g = torch.full((B, 70, 70, dim), 7.0, device="cuda")
+        g[:, :64, :64] = ln_ref.view(B, 64, 64, dim)
+        ln_ref = g.view(B, 5, 14, 5, 14, dim).permute(0, 1, 3, 2, 4, 5).reshape(rows, dim)
+    _close(xn, ln_ref, 1.2e-2, f"res+ln K={K} partition={partition}: normalised rows")
+
+
 def test_gemm_patch_pos():
     from ullsam_b200 import _lib, ops
 

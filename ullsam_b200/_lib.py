@@ -17,6 +17,7 @@ OK = 0
 F32, BF16, F16 = 0, 1, 2
 
 EPI_BF16, EPI_RES_F32, EPI_QKV, EPI_PATCH, EPI_LN_BF16, EPI_LN_NCHW, EPI_F32 = range(7)
+EPI_RES_LN = 11  # +residual fp32 and the LayerNorm that follows it -> bf16 (optionally window-partitioned)
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
 
@@ -78,6 +79,8 @@ class GemmDesc(C.Structure):
         ("ln_b", C.c_void_p),
         ("ln_eps", C.c_float),
         ("hw", C.c_int32),
+        ("out2", C.c_void_p),
+        ("ln_partition", C.c_int32),
     ]
 
 

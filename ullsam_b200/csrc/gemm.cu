@@ -122,8 +122,15 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
   if (e) return e;
   // Large plain GEMMs with 256-wide N tiles run on CTA pairs (each CTA loads only half of the W tile)
   static const bool pair_disabled = getenv("ULLSAM_GEMM_NO_PAIR") != nullptr;
-  const bool pair = !pair_disabled && bn == 256 && !p.a_conv3 && p.M >= 4096 &&
-                    (epi == EPI_BF16 || epi == EPI_GELU_BF16 || epi == EPI_RES_F32 || epi == EPI_QKV);
+  if (epi == EPI_RES_LN) {
+    if (bn != 256 || p.a_conv3 || p.M < 4096 || p.N > 1024)
+      return "gemm: EPI_RES_LN needs N % 256 == 0, N <= 1024, a plain A matrix and M >= 4096";
+    if (!p.out2 || !p.ln_w || !p.ln_b || !p.residual) return "gemm: EPI_RES_LN needs residual, ln_w, ln_b and out2";
+    if (p.ln_partition && p.M % 4096 != 0) return "gemm: EPI_RES_LN window partition needs whole 64x64 token grids";
+  }
+  const bool pair = (epi == EPI_RES_LN) ||
+                    (!pair_disabled && bn == 256 && !p.a_conv3 && p.M >= 4096 &&
+                     (epi == EPI_BF16 || epi == EPI_GELU_BF16 || epi == EPI_RES_F32 || epi == EPI_QKV));
   e = make_tmap_2d_bf16(&tb, W, (uint64_t)p.N, (uint64_t)p.K, pair ? 128 : bn, GEMM_BK);
   if (e) return e;
   if (pair) {
@@ -136,6 +143,7 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
       case EPI_RES_F32:
         return (ew16 & 2) ? launch_pair<EPI_RES_F32, 16>(ta, tb, p, num_sms, stream)
                           : launch_pair<EPI_RES_F32, 8>(ta, tb, p, num_sms, stream);
+      case EPI_RES_LN: return launch_pair<EPI_RES_LN, 8>(ta, tb, p, num_sms, stream);
       default:
         return (ew16 & 4) ? launch_pair<EPI_QKV, 16>(ta, tb, p, num_sms, stream)
                           : launch_pair<EPI_QKV, 8>(ta, tb, p, num_sms, stream);

@@ -22,6 +22,12 @@ enum EpiMode : int {
   EPI_MASK = 9,     // ConvT(64->32,k2s2) + GELU, contracted with hyper_in -> mask logits         (mask_decoder.py:57-58,144)
   EPI_GELU_BF16 = 10,  // EPI_BF16 with the exact-erf GELU resolved at compile time (MLPBlock.lin1, common.py:21-26);
                        // selected internally when EPI_BF16 is launched with act == ACT_GELU
+  EPI_RES_LN = 11,  // EPI_RES_F32 + the LayerNorm that FOLLOWS the residual add (Block: norm2 after the attention
+                    // branch, the next block's norm1 after the MLP branch, image_encoder.py:166-182) fused in: the CTA pair
+                    // walks the N tiles of one 256-row block back to back, accumulates the row statistics on the way,
+                    // re-reads the rows it has just written (L2) and stores out2 = bf16 LN(x) (optionally in
+                    // window-partitioned row order, image_encoder.py:243-264) — saves the HBM round trip of a separate
+                    // LayerNorm kernel
 };
 // EPI_BF16 / EPI_F32 also add pos[row % pos_rows][n] when p.pos != nullptr.
 
@@ -47,7 +53,9 @@ struct GemmParams {
   const float* ln_b;
   float ln_eps;
   int hw;  // tokens per image for the NCHW store
-  void* out2;          // EPI_LN_RES: bf16 copy of the normalised rows
+  void* out2;          // EPI_LN_RES / EPI_RES_LN: bf16 copy of the normalised rows
+  int ln_partition;    // EPI_RES_LN: 0 = out2 rows in token order, 1 = 14x14-window-partitioned order (25 windows of 196
+                       // rows per image; the zero pad rows are never written here)
   const float* hyper;  // EPI_MASK: hyper_in [R][4][32]
   int mask_m0;         // EPI_MASK: first mask channel written
   int mask_cnt;        // EPI_MASK: number of mask channels written (out is [R][mask_cnt][256][256] fp32)

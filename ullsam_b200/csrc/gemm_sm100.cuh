@@ -44,6 +44,60 @@ struct GemmSmem {
   static constexpr int kTotal = kStageOffset + EW * kStageBytesPerWarp + 1024 /* alignment slack */;
 };
 
+
+// Second pass of EPI_RES_LN for one warp: rows [row0, row0 + 32) x its 128-column half of each of the NT 256-wide N
+// tiles (exactly the elements this warp has just stored).  mean / rstd of row r live in lanes (r % 8) * 4 .. + 3 at
+// index r / 8.  The L2 reads are latency-bound, so the loads of RB rows x NT tiles are issued before any is consumed.
+template <int NT>
+ULLSAM_DEVICE void res_ln_second_pass(const GemmParams& p, int row0, int half, int lane, const float (&mean)[4],
+                                      const float (&rstd)[4]) {
+  constexpr int RB = 4;
+  const float* xsrc = reinterpret_cast<const float*>(p.out);
+  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(p.out2);
+  const int col0 = half * 128 + lane * 4;
+  float4 g4[NT], b4[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    g4[nt] = __ldg(reinterpret_cast<const float4*>(p.ln_w + nt * 256 + col0));
+    b4[nt] = __ldg(reinterpret_cast<const float4*>(p.ln_b + nt * 256 + col0));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int r0 = 0; r0 < 8; r0 += RB) {
+      float4 v4[RB][NT];
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb) {
+        const int grow = row0 + i * 8 + r0 + rb;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+          v4[rb][nt] = grow < p.M ? *reinterpret_cast<const float4*>(xsrc + static_cast<size_t>(grow) * p.ldc + nt * 256 + col0)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb) {
+        const float m = __shfl_sync(0xffffffffu, mean[i], (r0 + rb) * 4);
+        const float rs = __shfl_sync(0xffffffffu, rstd[i], (r0 + rb) * 4);
+        const int grow = row0 + i * 8 + r0 + rb;
+        if (grow >= p.M) continue;
+        size_t orow = grow;
+        if (p.ln_partition) {
+          const int b = grow >> 12, t = grow & 4095, y = t >> 6, x = t & 63;
+          const int wy = y / 14, wx = x / 14;
+          orow = static_cast<size_t>(b * 25 + wy * 5 + wx) * 196 + (y - wy * 14) * 14 + (x - wx * 14);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const float4 x4 = v4[rb][nt];
+          const uint32_t lo = pack_bf16(fmaf((x4.x - m) * rs, g4[nt].x, b4[nt].x), fmaf((x4.y - m) * rs, g4[nt].y, b4[nt].y));
+          const uint32_t hi = pack_bf16(fmaf((x4.z - m) * rs, g4[nt].z, b4[nt].z), fmaf((x4.w - m) * rs, g4[nt].w, b4[nt].w));
+          *reinterpret_cast<uint2*>(xn + orow * p.N + nt * 256 + col0) = make_uint2(lo, hi);
+        }
+      }
+    }
+  }
+}
+
 // EW epilogue warps: 8 (two per TMEM lane quadrant, BN/2 columns each) or 16 (four per quadrant, BN/4 columns each:
 // twice the warps to hide the TMEM / global latencies of the epilogue and to spread the GELU arithmetic).
 template <int BN, int EPI, int CG = 1, int EW = 8>
@@ -53,6 +107,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   static_assert(EW == 8 || (EPI != EPI_LN_BF16 && EPI != EPI_LN_NCHW && EPI != EPI_LN_RES && EPI != EPI_UP1 && EPI != EPI_MASK),
                 "the LayerNorm / decoder epilogues assume two warps per row");
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel is built for 256-wide N tiles");
+  static_assert(EPI != EPI_RES_LN || (BN == 256 && EW == 8), "EPI_RES_LN: 256-wide tiles, two 128-column halves per row");
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   constexpr int S = L::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -74,6 +129,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = p.K / GEMM_BK;
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;    // tiles are dealt to CTAs (CG=1) or CTA pairs (CG=2)
+  // i-th tile of this CTA (pair).  Default: round robin over the N-fastest tile list.  EPI_RES_LN: M-major — all N tiles
+  // of one row block are processed back to back by the same CTA pair, so its epilogue threads see whole rows.
+  constexpr bool kMMajor = (EPI == EPI_RES_LN);
+  constexpr bool kRes = (EPI == EPI_RES_F32 || EPI == EPI_RES_LN);
+  auto tile_at = [&](int i) -> int {
+    if constexpr (kMMajor) return (tile0 + (i / tiles_n) * tile_step) * tiles_n + (i % tiles_n);
+    else return tile0 + i * tile_step;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -112,7 +175,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      for (int pit = 0, tile = tile_at(0); tile < num_tiles; tile = tile_at(++pit)) {
         const int m_blk = (tile / tiles_n) * CG + cta_rank, n_blk = tile % tiles_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -148,8 +211,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       constexpr uint32_t idesc = make_idesc_bf16(CG * GEMM_BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+      for (int it = 0, tile = tile_at(0); tile < num_tiles; tile = tile_at(++it)) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -183,8 +245,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int row_in_tile = quad * 32 + lane;
     constexpr int COLS_PER_WARP = BN / (EW / 4);
     constexpr int NCHUNK = COLS_PER_WARP / 32;
-    int it = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+    float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};  // EPI_RES_LN: row sums / sums of squares
+    for (int it = 0, tile = tile_at(0); tile < num_tiles; tile = tile_at(++it)) {
       const int m_blk = (tile / tiles_n) * CG + cta_rank, n_blk = tile % tiles_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -424,7 +486,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // The addend (residual stream / pos_embed) of the whole 32-column chunk is requested up front,
           // so 8 independent 16-byte loads per lane are in flight while the accumulator is transposed.
           float4 add[2][4];
-          if constexpr (EPI == EPI_RES_F32 || EPI == EPI_PATCH) {
+          if constexpr (kRes || EPI == EPI_PATCH) {
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -432,7 +494,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int grow = tile_row0 + it * 8 + rr;
                 add[h][it] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (grow < p.M) {
-                  if constexpr (EPI == EPI_RES_F32)
+                  if constexpr (kRes)
                     add[h][it] = *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(grow) * p.ldc + n0 + h * 16 + cc * 4);
                   else
                     add[h][it] = __ldg(reinterpret_cast<const float4*>(
@@ -518,8 +580,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 float4 val = *reinterpret_cast<const float4*>(stage + r_in * 80 + cc * 16);
                 if (grow < p.M) {
                   const size_t off = static_cast<size_t>(grow) * p.ldc + n0 + h * 16 + cc * 4;
-                  if constexpr (EPI == EPI_RES_F32 || EPI == EPI_PATCH) {
+                  if constexpr (kRes || EPI == EPI_PATCH) {
                     val.x += add[h][it].x; val.y += add[h][it].y; val.z += add[h][it].z; val.w += add[h][it].w;
+                  }
+                  if constexpr (EPI == EPI_RES_LN) {
+                    st1[it] += (val.x + val.y) + (val.z + val.w);
+                    st2[it] = fmaf(val.x, val.x, fmaf(val.y, val.y, fmaf(val.z, val.z, fmaf(val.w, val.w, st2[it]))));
                   }
                   *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = val;
                 }
@@ -538,6 +604,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (lane == 0) {
         if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
         else mbar_arrive(&tempty_bar[acc]);
+      }
+      if constexpr (EPI == EPI_RES_LN) {
+        // ---- the LayerNorm that follows the residual add, once the last N tile of this row block is stored ----
+        if (n_blk == tiles_n - 1) {
+          const int rr = lane >> 2, cc = lane & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {  // the four 16-byte column slots of a row live in four adjacent lanes
+            st1[i] += __shfl_xor_sync(0xffffffffu, st1[i], 1);
+            st2[i] += __shfl_xor_sync(0xffffffffu, st2[i], 1);
+            st1[i] += __shfl_xor_sync(0xffffffffu, st1[i], 2);
+            st2[i] += __shfl_xor_sync(0xffffffffu, st2[i], 2);
+          }
+          float* s1 = scratch;        // [2 column halves][128 rows]
+          float* s2 = scratch + 256;
+          if (cc == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              s1[half * 128 + quad * 32 + i * 8 + rr] = st1[i];
+              s2[half * 128 + quad * 32 + i * 8 + rr] = st2[i];
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps (stats of the other column half)
+          float mean[4], rstd[4];
+          const float inv_n = 1.0f / static_cast<float>(p.N);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = quad * 32 + i * 8 + rr;
+            mean[i] = (s1[r] + s1[128 + r]) * inv_n;
+            const float var = fmaxf((s2[r] + s2[128 + r]) * inv_n - mean[i] * mean[i], 0.f);
+            rstd[i] = rsqrtf(var + p.ln_eps);
+            st1[i] = 0.f;
+            st2[i] = 0.f;
+          }
+          __syncwarp();  // every global store of this warp to its 32 rows (all N tiles) is visible to all its lanes
+          // second pass: re-read (L2), normalise, store bf16
+          const int row0 = m_blk * GEMM_BM + quad * 32;
+          if (tiles_n == 3) res_ln_second_pass<3>(p, row0, half, lane, mean, rstd);
+          else if (tiles_n == 4) res_ln_second_pass<4>(p, row0, half, lane, mean, rstd);
+          else if (tiles_n == 2) res_ln_second_pass<2>(p, row0, half, lane, mean, rstd);
+          else res_ln_second_pass<1>(p, row0, half, lane, mean, rstd);
+        }
       }
     }
   }

@@ -103,6 +103,7 @@ struct ullsam_handle {
   int enc_cap = 0;
   float* x = nullptr;
   bf16 *xn = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *ao = nullptr, *hid = nullptr;
+  bf16* xn_t = nullptr;  // LayerNorm outputs in token order (xn holds the window-partitioned ones: its pad rows stay zero)
   float* emb_f32 = nullptr;  // [cap,256,4096] when the caller wants bf16 output / host staging
   int dec_cap_r = 0, dec_cap_nt = 0;
   float *tokens = nullptr, *queries = nullptr, *tq = nullptr, *tk = nullptr, *tv = nullptr, *ta = nullptr, *tmp = nullptr,
@@ -416,21 +417,29 @@ int check_ready(ullsam_handle* h, int which) {
 
 int ensure_encoder_ws(ullsam_handle* h, int B) {
   if (B <= h->enc_cap) return ULLSAM_OK;
-  for (void* p : {(void*)h->x, (void*)h->xn, (void*)h->q, (void*)h->k, (void*)h->v, (void*)h->ao, (void*)h->hid, (void*)h->emb_f32})
+  for (void* p : {(void*)h->x, (void*)h->xn, (void*)h->xn_t, (void*)h->q, (void*)h->k, (void*)h->v, (void*)h->ao, (void*)h->hid,
+                  (void*)h->emb_f32})
     dfree(h, p);
   const size_t D = h->cfg.embed_dim, M = h->cfg.mlp_dim;
   const size_t tokw = static_cast<size_t>(B) * 4900, tok = static_cast<size_t>(B) * 4096;
   h->x = dalloc<float>(h, tok * D);
   h->xn = dalloc<bf16>(h, tokw * D);
+  h->xn_t = dalloc<bf16>(h, tok * D);
   h->q = dalloc<bf16>(h, tokw * D);
   h->k = dalloc<bf16>(h, tokw * D);
   h->v = dalloc<bf16>(h, tokw * D);
   h->ao = dalloc<bf16>(h, tok * D);
   h->hid = dalloc<bf16>(h, tok * (M > 768 ? M : 768));
   h->emb_f32 = dalloc<float>(h, tok * 256);
-  if (!h->x || !h->xn || !h->q || !h->k || !h->v || !h->ao || !h->hid || !h->emb_f32) {
+  if (!h->x || !h->xn || !h->xn_t || !h->q || !h->k || !h->v || !h->ao || !h->hid || !h->emb_f32) {
     h->enc_cap = 0;
     return fail(h, ULLSAM_ERR_NOMEM, "cudaMalloc failed for the encoder workspace");
+  }
+  // window_partition's zero pad rows (image_encoder.py:257-259): the fused residual+LayerNorm epilogue only writes the
+  // real rows of this buffer and nothing else ever writes the pad rows, so they are cleared once here
+  if (cudaMemset(h->xn, 0, tokw * D * sizeof(bf16)) != cudaSuccess) {
+    h->enc_cap = 0;
+    return fail(h, ULLSAM_ERR_CUDA, "cudaMemset failed for the encoder workspace");
   }
   h->enc_cap = B;
   return ULLSAM_OK;
@@ -504,50 +513,73 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
     CKS(launch_gemm(EPI_PATCH, h->hid, h->patch_w, p, sms, st));
     mark(h, PC_PATCH, st, 2);
   }
+  // The LayerNorms that follow a residual add (norm2 after the attention branch, the next block's norm1 after the MLP
+  // branch) CAN ride on the epilogue of the GEMM that performs the add (EPI_RES_LN).  Measured on B200 (ViT-B, batch
+  // 32) it does not pay: the epilogue has to re-read the rows through L2 once their statistics are complete, those
+  // 403 MB per GEMM arrive in synchronized bursts that stall the tensor pipe, and lin2 / proj lose more (+155 / +135 us
+  // per launch) than the LayerNorm kernel they replace costs (97 us at 96 % of the HBM roofline).  So the default is
+  // one LayerNorm kernel per norm; ULLSAM_LN_FUSION=1 (norm1 on lin2) / =3 (also norm2 on proj) select the fused path.
+  static const int fuse_env = getenv("ULLSAM_LN_FUSION") ? atoi(getenv("ULLSAM_LN_FUSION")) : 0;
+  // (the fused epilogue is built for 256-wide N tiles of at most 1024 columns: ViT-B and ViT-L)
+  const bool fusable = D % 256 == 0 && D <= 1024;
+  const bool fuse_ln1 = fusable && (fuse_env & 1), fuse_ln2 = fusable && (fuse_env & 2);
   for (int i = 0; i < c.depth; ++i) {
     const EncBlock& b = h->blocks[i];
     const int win = b.global ? 0 : c.window_size;
     const int Mq = b.global ? tok : tokw, T = b.global ? 4096 : 196;
-    // norm1 (+ window_partition)
-    CKS(launch_layernorm(h->x, b.ln1_w, b.ln1_b, c.enc_ln_eps, Bc, 64, D, win, h->xn, st));
-    mark(h, PC_LN, st);
+    bf16* xin = b.global ? h->xn_t : h->xn;   // norm1 output: token order / window-partitioned order
+    if (i == 0 || !fuse_ln1) {
+      // norm1 (+ window_partition)
+      CKS(launch_layernorm(h->x, b.ln1_w, b.ln1_b, c.enc_ln_eps, Bc, 64, D, win, xin, st));
+      mark(h, PC_LN, st);
+    }
     {  // qkv + head split
       GemmParams p = gp(Mq, 3 * D, D);
       p.bias = b.qkv_b; p.q = h->q; p.k = h->k; p.v = h->v; p.T = T; p.heads = heads;
-      CKS(launch_gemm(EPI_QKV, h->xn, b.qkv_w, p, sms, st));
+      CKS(launch_gemm(EPI_QKV, xin, b.qkv_w, p, sms, st));
       mark(h, PC_GEMM_QKV, st);
     }
     // attention (+ rel-pos bias, + window_unpartition)
     CKS(launch_attention(h->q, h->k, h->v, b.relh, b.relw, b.global ? Bc : Bc * 25, heads, b.global ? 64 : 14, h->ao, st));
     mark(h, b.global ? PC_ATTN_GLOBAL : PC_ATTN_WIN, st);
-    {  // proj + residual
+    {  // proj + residual (+ norm2)
       GemmParams p = gp(tok, D, D);
       p.bias = b.proj_b; p.out = h->x; p.residual = h->x;
-      CKS(launch_gemm(EPI_RES_F32, h->ao, b.proj_w, p, sms, st));
+      if (fuse_ln2) {
+        p.ln_w = b.ln2_w; p.ln_b = b.ln2_b; p.ln_eps = c.enc_ln_eps; p.out2 = h->xn_t; p.ln_partition = 0;
+      }
+      CKS(launch_gemm(fuse_ln2 ? EPI_RES_LN : EPI_RES_F32, h->ao, b.proj_w, p, sms, st));
       mark(h, PC_GEMM_PROJ, st);
     }
-    // norm2 + MLP + residual
-    CKS(launch_layernorm(h->x, b.ln2_w, b.ln2_b, c.enc_ln_eps, Bc, 64, D, 0, h->xn, st));
-    mark(h, PC_LN, st);
-    {
+    if (!fuse_ln2) {
+      CKS(launch_layernorm(h->x, b.ln2_w, b.ln2_b, c.enc_ln_eps, Bc, 64, D, 0, h->xn_t, st));
+      mark(h, PC_LN, st);
+    }
+    {  // MLP
       GemmParams p = gp(tok, MD, D);
       p.bias = b.lin1_b; p.out = h->hid; p.act = ACT_GELU;
-      CKS(launch_gemm(EPI_BF16, h->xn, b.lin1_w, p, sms, st));
+      CKS(launch_gemm(EPI_BF16, h->xn_t, b.lin1_w, p, sms, st));
       mark(h, PC_GEMM_LIN1, st);
     }
-    {
+    {  // lin2 + residual (+ the next block's norm1 and window_partition)
       GemmParams p = gp(tok, D, MD);
       p.bias = b.lin2_b; p.out = h->x; p.residual = h->x;
-      CKS(launch_gemm(EPI_RES_F32, h->hid, b.lin2_w, p, sms, st));
+      const bool fuse_next = fuse_ln1 && i + 1 < c.depth;
+      if (fuse_next) {
+        const EncBlock& nb = h->blocks[i + 1];
+        p.ln_w = nb.ln1_w; p.ln_b = nb.ln1_b; p.ln_eps = c.enc_ln_eps;
+        p.out2 = nb.global ? h->xn_t : h->xn; p.ln_partition = nb.global ? 0 : 1;
+      }
+      CKS(launch_gemm(fuse_next ? EPI_RES_LN : EPI_RES_F32, h->hid, b.lin2_w, p, sms, st));
       mark(h, PC_GEMM_LIN2, st);
     }
   }
   // neck: 1x1 conv -> LayerNorm2d -> 3x3 conv -> LayerNorm2d, NCHW out
-  CKS(launch_cast_f32_bf16(h->x, static_cast<size_t>(tok) * D, h->xn, st));
+  CKS(launch_cast_f32_bf16(h->x, static_cast<size_t>(tok) * D, h->xn_t, st));
   {
     GemmParams p = gp(tok, 256, D);
     p.out = h->q; p.ln_w = h->neck1_w; p.ln_b = h->neck1_b; p.ln_eps = 1e-6f;
-    CKS(launch_gemm(EPI_LN_BF16, h->xn, h->neck0_w, p, sms, st));
+    CKS(launch_gemm(EPI_LN_BF16, h->xn_t, h->neck0_w, p, sms, st));
   }
   {
     GemmParams p = gp(tok, 256, 9 * 256);

@@ -38,9 +38,11 @@ def gemm(
     ln_eps: float = 1e-6,
     hw: int = 4096,
     conv3: bool = False,
+    out2: Optional[torch.Tensor] = None,
+    ln_partition: bool = False,
 ) -> Optional[torch.Tensor]:
     """C = A[M,K] @ W[N,K]^T with the epilogue selected by ``epi`` (see include/ullsam.h)."""
-    _require_cuda(a, w, bias, out, residual, pos, ln_w, ln_b)
+    _require_cuda(a, w, bias, out, residual, pos, ln_w, ln_b, out2)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
     N, K = w.shape
     if conv3:
@@ -72,6 +74,7 @@ def gemm(
     d.pos = ptr(pos)
     d.pos_rows = pos.shape[0] if pos is not None else 0
     d.ln_w, d.ln_b, d.ln_eps, d.hw = ptr(ln_w), ptr(ln_b), ln_eps, hw
+    d.out2, d.ln_partition = ptr(out2), int(ln_partition)
     check(_lib.load().ullsam_op_gemm(C.byref(d), current_stream_ptr(a.device)), what="ullsam_op_gemm")
     return out
 
