@@ -48,6 +48,33 @@ def test_global_attention(rel_scale):
     assert err < 2e-2
 
 
+@pytest.mark.parametrize("growth", [6.0, 40.0])
+def test_global_attention_moving_row_maximum(growth):
+    """Scores that keep growing along the key axis (by `growth` nats in total, and in jumps inside key tiles), so the
+    running reference point of the online softmax has to move many times, in the middle of tiles as well as between
+    them: exercises the O / row-sum / stored-P rescaling of the fused kernel.  The softmax of every row is dominated by
+    the last keys; the reference is the fp32 formula (image_encoder.py:224-240)."""
+    from ullsam_b200 import ops
+
+    G, heads, grid = 1, 2, 64
+    q, k, v, rel_h, rel_w = _inputs(G, heads, grid, 17, 0.1)
+    T = grid * grid
+    u = torch.nn.functional.normalize(torch.randn(64, device="cuda"), dim=0)
+    ramp = torch.linspace(0.0, 1.0, T, device="cuda")
+    steps = (torch.arange(T, device="cuda") // 37).float() / (T // 37)      # jumps that are not aligned with key tiles
+    qf = q.float() * 0.3 + 8.0 * u                                         # every query has a large component along u
+    kf = k.float() * 0.3 + (growth * (0.5 * ramp + 0.5 * steps))[None, None, :, None] * u
+    q, k = qf.bfloat16(), kf.bfloat16()
+    out = ops.attention(q, k, v, rel_h, rel_w, grid)
+    torch.cuda.synchronize()
+    ref = _ref_attention(q.float(), k.float(), v.float(), rel_h, rel_w, grid)
+    ref = ref.permute(0, 2, 1, 3).reshape(G, 64, 64, heads * 64)
+    err = (out.float() - ref).abs().max().item()
+    print(f"global growth={growth}: max|err|={err:.3e} ref max={ref.abs().max().item():.3e}")
+    assert torch.isfinite(out.float()).all()
+    assert err < 3e-2
+
+
 @pytest.mark.parametrize("rel_scale", [0.0, 0.25])
 def test_windowed_attention(rel_scale):
     from ullsam_b200 import ops
