@@ -286,11 +286,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       if (leader) umma_commit(pro_mma_done);
       __syncwarp();
-      // NOTE: issuing QK(0) here, before the softmax warps have drained the prologue tables, was measured to be
-      // racy on B200 (run-to-run differences) even though the TMEM column ranges do not overlap; keep it after.
+      // windowed: S(0) (columns 0..111) does not touch the prologue tables (columns 128..191), so QK(0) is in flight
+      // while the softmax warps gather the bias; S(1) shares its columns with the tables and has to wait.  (global: the
+      // tables cover every S slot.)  test_attention_is_deterministic guards this hand-off.
+      if constexpr (!A::GLOBAL) issue_qk(0);
       mbar_wait(pro_consumed, 0);
       tc_fence_after();
-      for (int n = 0; n < NSLOT && n < NITEMS; ++n) issue_qk(n);
+      for (int n = A::GLOBAL ? 0 : 1; n < NSLOT && n < NITEMS; ++n) issue_qk(n);
       // Steady state, item n: O[qt] += P(n) V(j), then S(n + NSLOT) into the slot P(n) vacates (tcgen05 ops of one
       // thread execute in issue order).  The hand-over P(n) -> S(n + NSLOT) sits on the critical path of the softmax
       // warps, so everything that does not depend on P(n) — the operand barriers and all descriptor arithmetic —
