@@ -164,25 +164,49 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int row_base = gh * A::T;                  // first row of this (group, head) in q/k/v
   const int q_row0 = row_base + qblock * NROWS;
 
-  if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    mbar_init(pro_mma_done, 1);
-    mbar_init(pro_consumed, A::SM_WARPS);
-    for (int i = 0; i < KS; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+  // Barrier setup and the first TMA loads come from the same elected lane of the producer warp, BEFORE the CTA-wide
+  // sync: Q, the rel-pos tables and the K / V tiles whose ring slots are trivially free are already in flight while
+  // tensor memory is being allocated (the windowed kernel is a per-CTA latency chain, every hop counts).
+  constexpr int PRE_K = A::GLOBAL ? KS - 1 : (NT < KS ? NT : KS);   // global: the last slot still carries a table
+  constexpr int PRE_V = A::GLOBAL ? 0 : (NT < VS ? NT : VS);        // global: V has its own producer warp
+  if (warp == A::CTRL_WARP0) {
+    if (elect_one_sync()) {
+      mbar_init(q_full, 1);
+      mbar_init(pro_mma_done, 1);
+      mbar_init(pro_consumed, A::SM_WARPS);
+      for (int i = 0; i < KS; ++i) {
+        mbar_init(&k_full[i], 1);
+        mbar_init(&k_empty[i], 1);
+      }
+      for (int i = 0; i < VS; ++i) {
+        mbar_init(&v_full[i], 1);
+        mbar_init(&v_empty[i], 1);
+      }
+      for (int i = 0; i < NSLOT; ++i) mbar_init(&s_full[i], 1);
+      for (int i = 0; i < QT; ++i) {
+        mbar_init(&p_ready[i], 4 * A::SPLIT);
+        mbar_init(&o_done[2 * i], 1);
+        mbar_init(&o_done[2 * i + 1], 1);
+      }
+      fence_barrier_init();
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+      mbar_arrive_expect_tx(q_full, QT * A::QBYTES + 2 * A::NREL * 128);
+#pragma unroll
+      for (int qt = 0; qt < QT; ++qt) tma_load_2d(smem + A::OFF_Q + qt * A::QBYTES, &tmQ, q_full, 0, q_row0 + qt * 128);
+      tma_load_2d(smem + A::OFF_RELTAB_W, &tmRw, q_full, 0, 0);
+      tma_load_2d(smem + A::OFF_RELTAB_H, &tmRh, q_full, 0, 0);
+#pragma unroll
+      for (int j = 0; j < PRE_K; ++j) {
+        mbar_arrive_expect_tx(&k_full[j], A::KVSLOT);
+        tma_load_2d(smem + A::OFF_K + j * A::KVSLOT, &tmK, &k_full[j], 0, row_base + j * BN);
+      }
+#pragma unroll
+      for (int j = 0; j < PRE_V; ++j) {
+        mbar_arrive_expect_tx(&v_full[j], A::KVSLOT);
+        tma_load_2d(smem + A::OFF_V + j * A::KVSLOT, &tmV, &v_full[j], 0, row_base + j * BN);
+      }
     }
-    for (int i = 0; i < VS; ++i) {
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-    }
-    for (int i = 0; i < NSLOT; ++i) mbar_init(&s_full[i], 1);
-    for (int i = 0; i < QT; ++i) {
-      mbar_init(&p_ready[i], 4 * A::SPLIT);
-      mbar_init(&o_done[2 * i], 1);
-      mbar_init(&o_done[2 * i + 1], 1);
-    }
-    fence_barrier_init();
+    __syncwarp();
   }
   if (warp == A::CTRL_WARP0 + 1) {
     tmem_alloc(tmem_ptr_smem, A::TMEM_COLS);
@@ -200,19 +224,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp == A::CTRL_WARP0) {
     // =========================================== TMA producers ==========================================
-    // K stream (plus Q and the rel-pos tables) from this warp; the V stream has its own ring because V(j) is
-    // consumed a full tile later than K(j) — global: a separate warp, windowed (2 tiles): the same lane afterwards.
+    // the rest of the K stream from this warp; the V stream has its own ring because V(j) is consumed a full tile
+    // later than K(j) — global: a separate warp, windowed (2 tiles): everything was issued before the sync.
     // One lane chosen by elect.sync issues (see the note at the MMA issuer).
     if (elect_one_sync()) {
-      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK);
-      mbar_arrive_expect_tx(q_full, QT * A::QBYTES + 2 * A::NREL * 128);
-#pragma unroll
-      for (int qt = 0; qt < QT; ++qt) tma_load_2d(smem + A::OFF_Q + qt * A::QBYTES, &tmQ, q_full, 0, q_row0 + qt * 128);
-      tma_load_2d(smem + A::OFF_RELTAB_W, &tmRw, q_full, 0, 0);
-      tma_load_2d(smem + A::OFF_RELTAB_H, &tmRh, q_full, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < NT; ++j) {
+      int stage = PRE_K % KS;
+      uint32_t phase = (PRE_K / KS) & 1;
+      for (int j = PRE_K; j < NT; ++j) {
         if (A::GLOBAL && j == KS - 1) mbar_wait(pro_mma_done, 0);  // that slot still holds the rel_w table
         mbar_wait(&k_empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&k_full[stage], A::KVSLOT);
@@ -223,10 +241,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
   if (warp == (A::GLOBAL ? A::CTRL_WARP0 + 2 : A::CTRL_WARP0)) {
     if (elect_one_sync()) {
-      tma_prefetch_desc(&tmV);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < NT; ++j) {
+      int stage = PRE_V % VS;
+      uint32_t phase = (PRE_V / VS) & 1;
+      for (int j = PRE_V; j < NT; ++j) {
         if (A::GLOBAL && j == VS - 1) mbar_wait(pro_mma_done, 0);  // that slot still holds the rel_h table
         mbar_wait(&v_empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&v_full[stage], A::KVSLOT);
