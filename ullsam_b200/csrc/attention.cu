@@ -605,9 +605,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float* xch = reinterpret_cast<float*>(smem + A::OFF_XCH);  // [parity][hs][NROWS]
     const int bar_id = 1 + qt;                // named barrier of this query tile's 8 warps
 
-    float relw_reg[A::GLOBAL ? 1 : 14];
-    float relh_reg[A::GLOBAL ? 1 : 14];
-
     // ------------------------------------ prologue: gather the bias rows ------------------------------
     // hs == 0 scatters rel_w (Tw[row][qw - kw + GRID-1]), hs == 1 scatters rel_h (Th[row][qh - kh + GRID-1]).
     mbar_wait(pro_mma_done, 0);
@@ -639,15 +636,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     tc_fence_before();
     asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-    if constexpr (!A::GLOBAL) {
-#pragma unroll
-      for (int k = 0; k < 14; ++k) {
-        relw_reg[k] = relw_s[k * NROWS + tidq];
-        relh_reg[k] = relw_s[(14 + k) * NROWS + tidq];
-      }
-    } else {
-      relw_reg[0] = relh_reg[0] = 0.f;
-    }
+    // (windowed: the 2 x 14 bias values of the row stay in the scatter scratch, [14 + 14][NROWS] fp32, and are read
+    //  from there tile by tile — with 96 registers per thread a register copy ends up in local memory)
     if (lane == 0) mbar_arrive(pro_consumed);  // the prologue's TMEM columns may now be overwritten
 
     // ------------------------------------ main loop ---------------------------------------------------
@@ -699,15 +689,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mxp = fmaxf(mx0 + rh0, mx1 + rh1);
       } else {
         // columns hs*56 + i: key-grid row j*8 + hs*4 + i/14, key-grid column i % 14 (56 = 4 * 14)
-        float rht[4];
+        float rht[4], relw_reg[14];
 #pragma unroll
         for (int a4 = 0; a4 < 4; ++a4) {
-          const int kh = j * 8 + hs * 4 + a4;
-          float x = 0.f;
-#pragma unroll
-          for (int k = 0; k < 14; ++k) x = (k == kh) ? relh_reg[k] : x;
-          rht[a4] = x;
+          const int kh = j * 8 + hs * 4 + a4;   // (rows 14, 15 of the last tile are padding: masked below)
+          rht[a4] = relw_s[(14 + (kh < 14 ? kh : 13)) * NROWS + tidq];
         }
+#pragma unroll
+        for (int k = 0; k < 14; ++k) relw_reg[k] = relw_s[k * NROWS + tidq];
         const int valid = ((j == NT - 1) ? (A::T - (NT - 1) * BN) : BN) - hs * HALF;  // valid columns of this half
 #pragma unroll
         for (int i = 0; i < HALF; ++i) {
