@@ -467,7 +467,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // The TMEM load of chunk c+1 is in flight while chunk c is processed (two register buffers, loop fully
         // unrolled).  The GELU variant keeps the rolled loop: its per-chunk body is ~600 instructions and four
         // copies of it fall out of the instruction cache (measured: 972 -> 850 TFLOP/s when unrolled).
-        constexpr bool kPipe = (EPI != EPI_GELU_BF16);
+        constexpr bool kPipe = (EPI != EPI_GELU_BF16) && EW == 8;  // (16 epilogue warps: 96 registers, no room for two buffers)
         uint32_t vbuf[2][32];
         if constexpr (kPipe) {
           tmem_ld32(taddr0, vbuf[0]);
