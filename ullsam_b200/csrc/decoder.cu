@@ -137,92 +137,99 @@ __global__ void __launch_bounds__(256) tok_ln_kernel(const float* __restrict__ x
 }
 
 // ---------------------------------------------------------------------------------------------
-// token -> image cross attention (transformer.py:166-170, 102-105), internal dim 128 = 8 heads x 16.
-//   scores : S[r][h][i][key] = q[r][i][h,:] . K[r][key][h,:] / 4
-//   av     : o[r][i][h,:]    = softmax_key(S) . V[r][key][h,:]
+// token -> image cross attention (transformer.py:166-170, 102-105), internal dim 128 = 8 heads x 16:
+//   o[r][i][h,:] = softmax_key( q[r][i][h,:] . K[r][key][h,:] / 4 ) . V[r][key][h,:]
 // K and V are columns [0,128) and [128,256) of the bf16 projection buffer kv[R*4096][ldkv].
+// One CTA per (head, prompt): the 4096 keys are spread over the 256 threads, every thread keeps an online softmax
+// (max, sum, 16-wide accumulator) for up to TG prompt tokens at once, so K and V are read ONCE per group of TG tokens
+// and the [R][8][Nt][4096] score tensor never exists; the partial results are merged through shared memory.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) t2i_scores_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
-                                                         int ldkv, int Nt, float* __restrict__ S) {
-  extern __shared__ float qs[];  // [Nt][16]
-  const int r = blockIdx.z, h = blockIdx.y;
-  const int key = blockIdx.x * 256 + threadIdx.x;
-  for (int idx = threadIdx.x; idx < Nt * 16; idx += 256)
-    qs[idx] = q[(static_cast<size_t>(r) * Nt + idx / 16) * 128 + h * 16 + (idx & 15)];
-  __syncthreads();
-  const uint4* kp = reinterpret_cast<const uint4*>(kv + (static_cast<size_t>(r) * 4096 + key) * ldkv + h * 16);
-  const uint4 k0 = kp[0], k1 = kp[1];
-  float kf[16];
-  const __nv_bfloat162* b0 = reinterpret_cast<const __nv_bfloat162*>(&k0);
-  const __nv_bfloat162* b1 = reinterpret_cast<const __nv_bfloat162*>(&k1);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 t0 = __bfloat1622float2(b0[j]), t1 = __bfloat1622float2(b1[j]);
-    kf[2 * j] = t0.x; kf[2 * j + 1] = t0.y; kf[8 + 2 * j] = t1.x; kf[8 + 2 * j + 1] = t1.y;
-  }
-  float* Sp = S + (static_cast<size_t>(r) * 8 + h) * Nt * 4096 + key;
-  for (int i = 0; i < Nt; ++i) {
-    float a = 0.f;
-#pragma unroll
-    for (int d = 0; d < 16; ++d) a += qs[i * 16 + d] * kf[d];
-    Sp[static_cast<size_t>(i) * 4096] = a * 0.25f;
-  }
-}
+constexpr int T2I_TG = 4;
 
-__global__ void __launch_bounds__(256) t2i_softmax_av_kernel(const float* __restrict__ S, const __nv_bfloat16* __restrict__ kv,
-                                                             int ldkv, int Nt, float* __restrict__ o) {
-  __shared__ float red[8][17];
-  const int i = blockIdx.x, h = blockIdx.y, r = blockIdx.z;
+__global__ void __launch_bounds__(256) t2i_attention_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
+                                                            int ldkv, int Nt, float* __restrict__ o) {
+  constexpr int TG = T2I_TG;
+  __shared__ float qs[TG][16];
+  __shared__ float red[8][TG][18];  // per warp and token: max, sum, acc[16]
+  const int h = blockIdx.x, r = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* Sp = S + ((static_cast<size_t>(r) * 8 + h) * Nt + i) * 4096;
-  float s[16];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    s[j] = Sp[j * 256 + threadIdx.x];
-    mx = fmaxf(mx, s[j]);
-  }
-  mx = warp_max(mx);
-  if (lane == 0) red[warp][0] = mx;
-  __syncthreads();
-  mx = red[0][0];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w][0]);
-  __syncthreads();
-  float acc[16];
-#pragma unroll
-  for (int d = 0; d < 16; ++d) acc[d] = 0.f;
-  float sum = 0.f;
-#pragma unroll 4
-  for (int j = 0; j < 16; ++j) {
-    const float p = expf(s[j] - mx);
-    sum += p;
-    const int key = j * 256 + threadIdx.x;
-    const uint4* vp = reinterpret_cast<const uint4*>(kv + (static_cast<size_t>(r) * 4096 + key) * ldkv + 128 + h * 16);
-    const uint4 v0 = vp[0], v1 = vp[1];
-    const __nv_bfloat162* b0 = reinterpret_cast<const __nv_bfloat162*>(&v0);
-    const __nv_bfloat162* b1 = reinterpret_cast<const __nv_bfloat162*>(&v1);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float2 t0 = __bfloat1622float2(b0[u]), t1 = __bfloat1622float2(b1[u]);
-      acc[2 * u] += p * t0.x; acc[2 * u + 1] += p * t0.y;
-      acc[8 + 2 * u] += p * t1.x; acc[8 + 2 * u + 1] += p * t1.y;
+  for (int i0 = 0; i0 < Nt; i0 += TG) {
+    const int ng = (Nt - i0 < TG) ? (Nt - i0) : TG;
+    __syncthreads();
+    if (threadIdx.x < TG * 16) {
+      const int i = threadIdx.x >> 4, d = threadIdx.x & 15;
+      qs[i][d] = (i < ng) ? q[(static_cast<size_t>(r) * Nt + i0 + i) * 128 + h * 16 + d] * 0.25f : 0.f;  // 1/sqrt(16)
     }
-  }
-  sum = warp_sum(sum);
+    __syncthreads();
+    float m[TG], l[TG], acc[TG][16];
 #pragma unroll
-  for (int d = 0; d < 16; ++d) acc[d] = warp_sum(acc[d]);
-  if (lane == 0) {
-    red[warp][16] = sum;
+    for (int i = 0; i < TG; ++i) {
+      m[i] = -INFINITY;
+      l[i] = 0.f;
 #pragma unroll
-    for (int d = 0; d < 16; ++d) red[warp][d] = acc[d];
-  }
-  __syncthreads();
-  if (threadIdx.x < 16) {
-    float t = 0.f, a = 0.f;
+      for (int d = 0; d < 16; ++d) acc[i][d] = 0.f;
+    }
+#pragma unroll 1
+    for (int jj = 0; jj < 16; ++jj) {
+      const int key = jj * 256 + threadIdx.x;
+      const uint4* kp = reinterpret_cast<const uint4*>(kv + (static_cast<size_t>(r) * 4096 + key) * ldkv + h * 16);
+      const uint4* vp = kp + 16;  // + 128 bf16
+      const uint4 k0 = kp[0], k1 = kp[1], v0 = vp[0], v1 = vp[1];
+      float kf[16], vf[16];
+      const __nv_bfloat162* a0 = reinterpret_cast<const __nv_bfloat162*>(&k0);
+      const __nv_bfloat162* a1 = reinterpret_cast<const __nv_bfloat162*>(&k1);
+      const __nv_bfloat162* c0 = reinterpret_cast<const __nv_bfloat162*>(&v0);
+      const __nv_bfloat162* c1 = reinterpret_cast<const __nv_bfloat162*>(&v1);
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { t += red[w][16]; a += red[w][threadIdx.x]; }
-    o[(static_cast<size_t>(r) * Nt + i) * 128 + h * 16 + threadIdx.x] = a / t;
+      for (int u = 0; u < 4; ++u) {
+        const float2 t0 = __bfloat1622float2(a0[u]), t1 = __bfloat1622float2(a1[u]);
+        kf[2 * u] = t0.x; kf[2 * u + 1] = t0.y; kf[8 + 2 * u] = t1.x; kf[8 + 2 * u + 1] = t1.y;
+        const float2 w0 = __bfloat1622float2(c0[u]), w1 = __bfloat1622float2(c1[u]);
+        vf[2 * u] = w0.x; vf[2 * u + 1] = w0.y; vf[8 + 2 * u] = w1.x; vf[8 + 2 * u + 1] = w1.y;
+      }
+#pragma unroll
+      for (int i = 0; i < TG; ++i) {
+        float sc = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) sc = fmaf(qs[i][d], kf[d], sc);
+        const float mn = fmaxf(m[i], sc);
+        const float corr = __expf(m[i] - mn), p = __expf(sc - mn);
+        l[i] = l[i] * corr + p;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[i][d] = fmaf(acc[i][d], corr, p * vf[d]);
+        m[i] = mn;
+      }
+    }
+    // merge: warp first (common max, rescale, sum), then the 8 warps through shared memory
+#pragma unroll
+    for (int i = 0; i < TG; ++i) {
+      const float wm = warp_max(m[i]);
+      const float sc = __expf(m[i] - wm);
+      const float ls = warp_sum(l[i] * sc);
+      if (lane == 0) { red[warp][i][0] = wm; red[warp][i][1] = ls; }
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        const float a = warp_sum(acc[i][d] * sc);
+        if (lane == 0) red[warp][i][2 + d] = a;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < TG * 16) {
+      const int i = threadIdx.x >> 4, d = threadIdx.x & 15;
+      if (i < ng) {
+        float gm = red[0][i][0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) gm = fmaxf(gm, red[w][i][0]);
+        float L = 0.f, A = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const float sc = __expf(red[w][i][0] - gm);
+          L = fmaf(red[w][i][1], sc, L);
+          A = fmaf(red[w][i][2 + d], sc, A);
+        }
+        o[(static_cast<size_t>(r) * Nt + i0 + i) * 128 + h * 16 + d] = A / L;
+      }
+    }
   }
 }
 
@@ -234,13 +241,18 @@ __global__ void __launch_bounds__(256) t2i_softmax_av_kernel(const float* __rest
 __global__ void __launch_bounds__(256) i2t_attention_kernel(const __nv_bfloat16* __restrict__ proj, int ldp, int q_col,
                                                             const float* __restrict__ k, const float* __restrict__ v,
                                                             int Nt, __nv_bfloat16* __restrict__ out) {
-  extern __shared__ float kvs[];  // k [Nt][128], v [Nt][128]
+  // k, v in shared memory as [Nt][8 heads][20]: the 16 floats of a head padded to 20, so that the eight heads of a
+  // token (the 8 threads of one 128-bit load phase) hit eight different 16-byte bank groups
+  extern __shared__ __align__(16) float kvs[];
+  constexpr int HS = 20, TS = 8 * HS;
   const int r = blockIdx.y;
   float* ks = kvs;
-  float* vs = kvs + Nt * 128;
+  float* vs = kvs + Nt * TS;
   for (int idx = threadIdx.x; idx < Nt * 128; idx += 256) {
-    ks[idx] = k[static_cast<size_t>(r) * Nt * 128 + idx];
-    vs[idx] = v[static_cast<size_t>(r) * Nt * 128 + idx];
+    const int j = idx >> 7, c = idx & 127;
+    const int o = j * TS + (c >> 4) * HS + (c & 15);
+    ks[o] = k[static_cast<size_t>(r) * Nt * 128 + idx] * 0.25f;   // 1/sqrt(16) folded into k
+    vs[o] = v[static_cast<size_t>(r) * Nt * 128 + idx];
   }
   __syncthreads();
   const int tok = blockIdx.x * 32 + (threadIdx.x >> 3);
@@ -254,23 +266,32 @@ __global__ void __launch_bounds__(256) i2t_attention_kernel(const __nv_bfloat16*
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 t0 = __bfloat1622float2(b0[j]), t1 = __bfloat1622float2(b1[j]);
-    qf[2 * j] = t0.x * 0.25f; qf[2 * j + 1] = t0.y * 0.25f;
-    qf[8 + 2 * j] = t1.x * 0.25f; qf[8 + 2 * j + 1] = t1.y * 0.25f;
+    qf[2 * j] = t0.x; qf[2 * j + 1] = t0.y;
+    qf[8 + 2 * j] = t1.x; qf[8 + 2 * j + 1] = t1.y;
   }
   float m = -INFINITY, l = 0.f, acc[16];
 #pragma unroll
   for (int d = 0; d < 16; ++d) acc[d] = 0.f;
   for (int j = 0; j < Nt; ++j) {
-    const float* kj = ks + j * 128 + h * 16;
+    const float4* kj = reinterpret_cast<const float4*>(ks + j * TS + h * HS);
     float s = 0.f;
 #pragma unroll
-    for (int d = 0; d < 16; ++d) s += qf[d] * kj[d];
+    for (int d4 = 0; d4 < 4; ++d4) {
+      const float4 kk = kj[d4];
+      s += qf[4 * d4] * kk.x + qf[4 * d4 + 1] * kk.y + qf[4 * d4 + 2] * kk.z + qf[4 * d4 + 3] * kk.w;
+    }
     const float mn = fmaxf(m, s);
     const float corr = expf(m - mn), p = expf(s - mn);
     l = l * corr + p;
-    const float* vj = vs + j * 128 + h * 16;
+    const float4* vj = reinterpret_cast<const float4*>(vs + j * TS + h * HS);
 #pragma unroll
-    for (int d = 0; d < 16; ++d) acc[d] = acc[d] * corr + p * vj[d];
+    for (int d4 = 0; d4 < 4; ++d4) {
+      const float4 vv = vj[d4];
+      acc[4 * d4] = acc[4 * d4] * corr + p * vv.x;
+      acc[4 * d4 + 1] = acc[4 * d4 + 1] * corr + p * vv.y;
+      acc[4 * d4 + 2] = acc[4 * d4 + 2] * corr + p * vv.z;
+      acc[4 * d4 + 3] = acc[4 * d4 + 3] * corr + p * vv.w;
+    }
     m = mn;
   }
   const float inv = 1.0f / l;
@@ -371,25 +392,23 @@ const char* launch_tok_ln(const float* x, const float* gamma, const float* beta,
   return last_err();
 }
 
-const char* launch_t2i_attention(const float* q, const __nv_bfloat16* kv, int ldkv, int R, int Nt, float* S, float* o,
+const char* launch_t2i_attention(const float* q, const __nv_bfloat16* kv, int ldkv, int R, int Nt, float* o,
                                  cudaStream_t stream) {
-  t2i_scores_kernel<<<dim3(16, 8, R), 256, Nt * 16 * sizeof(float), stream>>>(q, kv, ldkv, Nt, S);
-  if (const char* e = last_err()) return e;
-  t2i_softmax_av_kernel<<<dim3(Nt, 8, R), 256, 0, stream>>>(S, kv, ldkv, Nt, o);
+  t2i_attention_kernel<<<dim3(8, R), 256, 0, stream>>>(q, kv, ldkv, Nt, o);
   return last_err();
 }
 
 const char* launch_i2t_attention(const __nv_bfloat16* proj, int ldp, int q_col, const float* k, const float* v, int R,
                                  int Nt, __nv_bfloat16* out, cudaStream_t stream) {
-  if (Nt > 40) {
+  if (Nt > 32) {
     static bool configured = false;
     if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(i2t_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 256 * 4);
+      cudaError_t e = cudaFuncSetAttribute(i2t_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 320 * 4);
       if (e != cudaSuccess) return cudaGetErrorString(e);
       configured = true;
     }
   }
-  i2t_attention_kernel<<<dim3(128, R), 256, Nt * 256 * sizeof(float), stream>>>(proj, ldp, q_col, k, v, Nt, out);
+  i2t_attention_kernel<<<dim3(128, R), 256, Nt * 320 * sizeof(float), stream>>>(proj, ldp, q_col, k, v, Nt, out);
   return last_err();
 }
 

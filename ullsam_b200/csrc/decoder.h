@@ -28,7 +28,7 @@ const char* launch_tok_self_attn(const float* q, const float* k, const float* v,
 const char* launch_tok_ln(const float* x, const float* gamma, const float* beta, int rows, float eps, float* y,
                           cudaStream_t stream);
 // q fp32 [R][Nt][128]; kv bf16 [R*4096][ldkv] (K = cols 0..127, V = cols 128..255); S scratch fp32 [R][8][Nt][4096]
-const char* launch_t2i_attention(const float* q, const __nv_bfloat16* kv, int ldkv, int R, int Nt, float* S, float* o,
+const char* launch_t2i_attention(const float* q, const __nv_bfloat16* kv, int ldkv, int R, int Nt, float* o,
                                  cudaStream_t stream);
 // proj bf16 [R*4096][ldp] with the image-side queries at column q_col; k, v fp32 [R][Nt][128]; out bf16 [R*4096][128]
 const char* launch_i2t_attention(const __nv_bfloat16* proj, int ldp, int q_col, const float* k, const float* v, int R,

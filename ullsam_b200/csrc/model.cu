@@ -108,7 +108,7 @@ struct ullsam_handle {
   int dec_cap_r = 0, dec_cap_nt = 0;
   float *tokens = nullptr, *queries = nullptr, *tq = nullptr, *tk = nullptr, *tv = nullptr, *ta = nullptr, *tmp = nullptr,
         *thid = nullptr, *q128 = nullptr, *k128 = nullptr, *v128 = nullptr, *o128 = nullptr;
-  float *keys = nullptr, *S = nullptr, *hyp1 = nullptr, *hyp2 = nullptr, *hyper = nullptr, *iou1 = nullptr, *iou2 = nullptr,
+  float *keys = nullptr, *hyp1 = nullptr, *hyp2 = nullptr, *hyper = nullptr, *iou1 = nullptr, *iou2 = nullptr,
         *iou4 = nullptr;
   bf16 *keys_bf = nullptr, *proj = nullptr, *ao128 = nullptr, *pe_bf = nullptr, *up_h = nullptr;
   std::vector<float*> peproj;  // per layer [4096,384], final [4096,256]
@@ -452,7 +452,7 @@ int ensure_decoder_ws(ullsam_handle* h, int R, int Nt) {
   if (R < h->dec_cap_r) R = h->dec_cap_r;
   if (Nt < h->dec_cap_nt) Nt = h->dec_cap_nt;
   for (void* p : {(void*)h->tokens, (void*)h->queries, (void*)h->tq, (void*)h->tk, (void*)h->tv, (void*)h->ta, (void*)h->tmp,
-                  (void*)h->thid, (void*)h->q128, (void*)h->k128, (void*)h->v128, (void*)h->o128, (void*)h->keys, (void*)h->S,
+                  (void*)h->thid, (void*)h->q128, (void*)h->k128, (void*)h->v128, (void*)h->o128, (void*)h->keys,
                   (void*)h->hyp1, (void*)h->hyp2, (void*)h->hyper, (void*)h->iou1, (void*)h->iou2, (void*)h->iou4,
                   (void*)h->keys_bf, (void*)h->proj, (void*)h->ao128, (void*)h->pe_bf, (void*)h->up_h})
     dfree(h, p);
@@ -466,7 +466,6 @@ int ensure_decoder_ws(ullsam_handle* h, int R, int Nt) {
   h->q128 = dalloc<float>(h, rt * 128); h->k128 = dalloc<float>(h, rt * 128); h->v128 = dalloc<float>(h, rt * 128);
   h->o128 = dalloc<float>(h, rt * 128);
   h->keys = dalloc<float>(h, rk * 256);
-  h->S = dalloc<float>(h, rt * 8 * 4096);
   h->hyp1 = dalloc<float>(h, static_cast<size_t>(R) * 4 * 256); h->hyp2 = dalloc<float>(h, static_cast<size_t>(R) * 4 * 256);
   h->hyper = dalloc<float>(h, static_cast<size_t>(R) * 4 * 32);
   h->iou1 = dalloc<float>(h, static_cast<size_t>(R) * 256); h->iou2 = dalloc<float>(h, static_cast<size_t>(R) * 256);
@@ -477,7 +476,7 @@ int ensure_decoder_ws(ullsam_handle* h, int R, int Nt) {
   h->pe_bf = dalloc<bf16>(h, 4096 * 256);
   h->up_h = dalloc<bf16>(h, static_cast<size_t>(R) * 16384 * 64);
   bool ok = h->tokens && h->queries && h->tq && h->tk && h->tv && h->ta && h->tmp && h->thid && h->q128 && h->k128 &&
-            h->v128 && h->o128 && h->keys && h->S && h->hyp1 && h->hyp2 && h->hyper && h->iou1 && h->iou2 && h->iou4 &&
+            h->v128 && h->o128 && h->keys && h->hyp1 && h->hyp2 && h->hyper && h->iou1 && h->iou2 && h->iou4 &&
             h->keys_bf && h->proj && h->ao128 && h->pe_bf && h->up_h;
   for (int i = 0; i <= h->cfg.dec_depth; ++i) {
     h->peproj.push_back(dalloc<float>(h, 4096 * 384));
@@ -605,8 +604,8 @@ int t2i_block(ullsam_handle* h, int R, int Nt, const float* q_w, const float* q_
   const int M = R * Nt;
   CKS(launch_tok_linear(lin(h->queries, h->tokens, q_w, q_b, nullptr, h->q128, M, 128, 256), st));
   mark(h, PC_DEC_TOKENS, st, 1);
-  CKS(launch_t2i_attention(h->q128, h->proj, ldkv, R, Nt, h->S, h->o128, st));
-  mark(h, PC_DEC_ATTN, st, 2);
+  CKS(launch_t2i_attention(h->q128, h->proj, ldkv, R, Nt, h->o128, st));
+  mark(h, PC_DEC_ATTN, st, 1);
   CKS(launch_tok_linear(lin(h->o128, nullptr, o_w, o_b, h->queries, h->tmp, M, 256, 128), st));
   mark(h, PC_DEC_TOKENS, st, 1);
   CKS(launch_tok_ln(h->tmp, n_w, n_b, M, 1e-5f, h->queries, st));
