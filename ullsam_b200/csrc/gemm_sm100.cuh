@@ -327,7 +327,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         float* s_sq = scratch + 2 * 128;
         const size_t rbase = static_cast<size_t>(row_ok ? row : 0) * p.ldc;
         auto load_x = [&](int c, float (&f)[32]) {
-          uint32_t v[32];
+          uint32_t (&v)[32] = reinterpret_cast<uint32_t (&)[32]>(f);   // accumulator bits land in place
           tmem_ld32(taddr0 + c * 32, v);
           tmem_wait_ld();
           const int n0 = col0 + c * 32;
@@ -343,32 +343,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + r.w + b.w;
           }
         };
-        float part = 0.f;
+        // One pass for the statistics (sum and sum of squares together, one exchange with the other column half) and
+        // one for the output; the first KEEP chunks of the row stay in registers in between, the others are read again
+        // (TMEM + residual) — instead of three full passes.
+        constexpr int KEEP = NCHUNK < 2 ? NCHUNK : 2;
+        float xk[KEEP][32];
+        float s1 = 0.f, s2 = 0.f;
+        auto stats = [&](const float (&f)[32]) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            s1 += f[j];
+            s2 = fmaf(f[j], f[j], s2);
+          }
+        };
+#pragma unroll
+        for (int c = 0; c < KEEP; ++c) {
+          load_x(c, xk[c]);
+          stats(xk[c]);
+        }
 #pragma unroll 1
-        for (int c = 0; c < NCHUNK; ++c) {
+        for (int c = KEEP; c < NCHUNK; ++c) {
           float f[32];
           load_x(c, f);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) part += f[j];
+          stats(f);
         }
-        s_sum[half * 128 + row_in_tile] = part;
+        s_sum[half * 128 + row_in_tile] = s1;
+        s_sq[half * 128 + row_in_tile] = s2;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const float mean = (s_sum[row_in_tile] + s_sum[128 + row_in_tile]) * (1.0f / BN);
-        part = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < NCHUNK; ++c) {
-          float f[32];
-          load_x(c, f);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) part += (f[j] - mean) * (f[j] - mean);
-        }
-        s_sq[half * 128 + row_in_tile] = part;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float rstd = rsqrtf((s_sq[row_in_tile] + s_sq[128 + row_in_tile]) * (1.0f / BN) + p.ln_eps);
-#pragma unroll 1
-        for (int c = 0; c < NCHUNK; ++c) {
-          float f[32];
-          load_x(c, f);
+        const float var = fmaxf((s_sq[row_in_tile] + s_sq[128 + row_in_tile]) * (1.0f / BN) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.ln_eps);
+        auto emit = [&](float (&f)[32], int c) {
           const int n0 = col0 + c * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = (f[j] - mean) * rstd * __ldg(p.ln_w + n0 + j) + __ldg(p.ln_b + n0 + j);
@@ -382,7 +387,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               d2[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
                                  pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
           }
+        };
+#pragma unroll 1
+        for (int c = KEEP; c < NCHUNK; ++c) {   // (these read the residual again: before the kept chunks overwrite it?
+          float f[32];                          //  no — every chunk only touches its own columns)
+          load_x(c, f);
+          emit(f, c);
         }
+#pragma unroll
+        for (int c = 0; c < KEEP; ++c) emit(xk[c], c);
+        // (the scratch is written again only after the next tile's statistics pass, which every warp of the row pair
+        //  reaches after this barrier: add one more so a fast warp cannot overwrite s_sum before the slow one has read it)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       } else if constexpr (EPI == EPI_UP1) {
         // ---- columns = (ky,kx,co): each 64-wide group is one output pixel; LayerNorm2d(64) + GELU ----
         static_assert(EPI != EPI_UP1 || BN == 256, "EPI_UP1 needs BN == 256");
