@@ -95,9 +95,7 @@ struct AttCfg {
 
 // size-overloaded TMEM accessors (the piece size of the softmax is a compile-time knob)
 ULLSAM_DEVICE void tmem_ld_n(uint32_t a, uint32_t (&v)[16]) { tmem_ld16(a, v); }
-ULLSAM_DEVICE void tmem_ld_n(uint32_t a, uint32_t (&v)[32]) { tmem_ld32(a, v); }
 ULLSAM_DEVICE void tmem_st_n(uint32_t a, const uint32_t (&v)[8]) { tmem_st8(a, v); }
-ULLSAM_DEVICE void tmem_st_n(uint32_t a, const uint32_t (&v)[16]) { tmem_st16(a, v); }
 
 ULLSAM_DEVICE float ex2(float x) {
   float y;
@@ -127,9 +125,7 @@ ULLSAM_DEVICE float ex2_poly(float x) {
 #ifndef ULLSAM_ATT_REGS_CTRL
 #define ULLSAM_ATT_REGS_CTRL 56
 #endif
-#ifndef ULLSAM_ATT_PIECE
-#define ULLSAM_ATT_PIECE 16
-#endif
+#define ULLSAM_ATT_PIECE 16   // keys per piece of the exponentiation pass (32 measured slower: register pressure)
 #ifndef ULLSAM_ATT_POLY_MASK
 #define ULLSAM_ATT_POLY_MASK 0x00
 #endif
