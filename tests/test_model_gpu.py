@@ -67,6 +67,40 @@ def test_encoder_vs_reference_golden(ctx):
     assert e <= 1e-2
 
 
+def test_encoder_is_batch_invariant_across_chunks(ctx):
+    """Full-size property (BASELINE.json's batch of 32 and beyond): an image's embedding does not depend on where it
+    sits in the batch — 34 images (two 32-image workspace chunks: 32 + 2) made of two distinct images must reproduce the
+    2-image result bit for bit, every copy identical.  Exercises the chunking of Engine.encoder_forward, the tail tiles of
+    every GEMM and the persistent tile schedulers at the benchmark's size."""
+    eng, images = ctx["eng"], ctx["images"]
+    big = images[[0, 1] * 17].contiguous().cuda()
+    emb = eng.encoder_forward(big)
+    torch.cuda.synchronize()
+    assert emb.shape == (34, 256, 64, 64)
+    for i in range(34):
+        assert torch.equal(emb[i], ctx["emb"][i % 2]), f"image {i} differs from the 2-image run"
+
+
+def test_decoder_many_prompts_and_ragged_token_counts(ctx):
+    """Ragged prompt shapes: 1, 5 and 13 sparse tokens (Nt = 5 + Ns up to 18, more than one 4-token group of the fused
+    token->image attention, not a multiple of it) and 9 prompts on one image; every prompt must match the CPU oracle."""
+    eng, cfg, sd = ctx["eng"], ctx["cfg"], ctx["sd"]
+    emb = ctx["emb"][:1]
+    pe = O.dense_pe(sd, cfg)
+    gen = torch.Generator().manual_seed(5)
+    for P, Ns in ((9, 1), (2, 5), (3, 13)):
+        sparse = torch.randn(P, Ns, 256, generator=gen) * 0.5
+        dense = torch.randn(P, 256, 64, 64, generator=gen) * 0.05
+        with torch.no_grad():
+            m_ref, s_ref = O.decoder_forward(sd, ctx["emb_ref"][:1], pe, sparse, dense, False, cfg)
+        m, s = eng.decoder_forward(emb, pe.cuda(), sparse.cuda(), dense.cuda(), multimask_output=False)
+        torch.cuda.synchronize()
+        iou = min(mask_iou(m[i].cpu(), m_ref[i]) for i in range(P))
+        err = (s.cpu() - s_ref).abs().max().item()
+        print(f"P={P} Ns={Ns}: min mask IoU {iou:.4f}, iou-head err {err:.2e}")
+        assert m.shape == (P, 1, 256, 256) and iou >= 0.99 and err < 5e-3
+
+
 def test_encoder_bf16_io(ctx):
     eng = ctx["eng"]
     out = eng.encoder_forward(ctx["images"][:1].cuda().bfloat16(), out_dtype=torch.bfloat16)
