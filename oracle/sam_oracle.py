@@ -171,8 +171,8 @@ def dense_pe(sd: SD, cfg: SamConfig, prefix: str = "prompt_encoder.") -> torch.T
     """PromptEncoder.get_dense_pe, prompt_encoder.py:65-74, 230-241 -> [1, C, g, g]."""
     g = cfg.grid
     gauss = sd[prefix + "pe_layer.positional_encoding_gaussian_matrix"]
-    ys = (torch.arange(g, dtype=torch.float32) + 0.5) / g
-    xs = (torch.arange(g, dtype=torch.float32) + 0.5) / g
+    ys = (torch.arange(g, dtype=torch.float32, device=gauss.device) + 0.5) / g
+    xs = (torch.arange(g, dtype=torch.float32, device=gauss.device) + 0.5) / g
     coords = torch.stack([xs[None, :].expand(g, g), ys[:, None].expand(g, g)], dim=-1)
     return _pe_encoding(gauss, coords).permute(2, 0, 1)[None]
 
