@@ -188,6 +188,25 @@ int ullsam_op_attention(const void* q, const void* k, const void* v, const void*
 /* PatchEmbed's im2col (image_encoder.py:387-395): images [B,3,1024,1024] (dtype) -> bf16 [B*4096, 768]. */
 int ullsam_op_im2col(const void* images, int dtype, int B, void* patches_bf16, void* stream);
 
+/* ---- PromptEncoder on the device (the step upstream of the decoder) ---------------- */
+
+/* PositionEmbeddingRandom.forward == PromptEncoder.get_dense_pe without the batch dim (prompt_encoder.py:65-74, 230-241):
+ * gauss = pe_layer.positional_encoding_gaussian_matrix [2, F] fp32 -> out fp32 [2F, g, g]. */
+int ullsam_op_prompt_dense_pe(const float* gauss, int F, int g, float* out, void* stream);
+
+/* PromptEncoder._embed_points / _embed_boxes (prompt_encoder.py:76-103) -> sparse embeddings fp32 [P, Ns, 2F] with
+ * Ns = (coords ? Np + pad : 0) + (boxes ? 2 : 0).  coords [P, Np, 2] pixel XY, labels [P, Np] fp32 (-1 / 0 / 1),
+ * boxes [P, 4] XYXY; point_emb = point_embeddings.{0..3}.weight stacked [4, 2F]; not_a_point [2F].
+ * pad = 1 appends the padding point exactly as forward() does when no box is given (:171). */
+int ullsam_op_prompt_sparse(const float* gauss, int F, const float* point_emb, const float* not_a_point, const float* coords,
+                            const float* labels, int P, int Np, int pad, const float* boxes, float img_w, float img_h,
+                            float* out, void* stream);
+
+/* PromptEncoder._normalize_llm_hidden_states (prompt_encoder.py:131-151): x [P, C, HW] (dtype ULLSAM_F32 / ULLSAM_BF16)
+ * -> out fp32 [P, C, HW] = layer_norm over C (no affine, eps 1e-5) * llm_scale_factor[0] + llm_bias[0]. */
+int ullsam_op_prompt_llm_dense(const void* x, int dtype, int P, int C, int HW, const float* scale, const float* bias,
+                               float* out, void* stream);
+
 /* fp32 -> bf16 (count elements). */
 int ullsam_op_cast_bf16(const float* x, size_t count, void* y_bf16, void* stream);
 

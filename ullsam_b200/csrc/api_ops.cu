@@ -7,6 +7,7 @@
 #include "api_internal.h"
 #include "attention.h"
 #include "elementwise.h"
+#include "prompt.h"
 #include "gemm.h"
 
 namespace ullsam {
@@ -82,6 +83,29 @@ int ullsam_op_im2col(const void* images, int dtype, int B, void* patches_bf16, v
   if (dtype != ULLSAM_F32 && dtype != ULLSAM_BF16) return op_fail(ULLSAM_ERR_INVALID, "op_im2col: dtype must be f32 or bf16");
   const char* e = launch_im2col16(images, dtype == ULLSAM_BF16, B, 3, 1024, static_cast<__nv_bfloat16*>(patches_bf16),
                                   static_cast<cudaStream_t>(stream));
+  return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
+}
+
+int ullsam_op_prompt_dense_pe(const float* gauss, int F, int g, float* out, void* stream) {
+  if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_prompt_dense_pe: no sm_100 device");
+  const char* e = launch_prompt_pe_grid(gauss, F, g, out, static_cast<cudaStream_t>(stream));
+  return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
+}
+
+int ullsam_op_prompt_sparse(const float* gauss, int F, const float* point_emb, const float* not_a_point, const float* coords,
+                            const float* labels, int P, int Np, int pad, const float* boxes, float img_w, float img_h,
+                            float* out, void* stream) {
+  if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_prompt_sparse: no sm_100 device");
+  const char* e = launch_prompt_sparse(gauss, F, point_emb, not_a_point, coords, labels, P, Np, pad, boxes, img_w, img_h, out,
+                                       static_cast<cudaStream_t>(stream));
+  return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
+}
+
+int ullsam_op_prompt_llm_dense(const void* x, int dtype, int P, int C, int HW, const float* scale, const float* bias, float* out,
+                               void* stream) {
+  if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_prompt_llm_dense: no sm_100 device");
+  if (dtype != ULLSAM_F32 && dtype != ULLSAM_BF16) return op_fail(ULLSAM_ERR_INVALID, "op_prompt_llm_dense: dtype must be f32 or bf16");
+  const char* e = launch_prompt_llm_dense(x, dtype == ULLSAM_BF16, P, C, HW, scale, bias, out, static_cast<cudaStream_t>(stream));
   return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
 }
 

@@ -14,16 +14,17 @@ from torch import nn
 
 from .image_encoder import ImageEncoderViT
 from .mask_decoder import MaskDecoder
+from .prompt_encoder import PromptEncoder
 from .transformer import TwoWayTransformer
 
-__all__ = ["ImageEncoderViT", "MaskDecoder", "TwoWayTransformer", "install", "accelerate", "convert_encoder",
-           "convert_decoder"]
+__all__ = ["ImageEncoderViT", "MaskDecoder", "PromptEncoder", "TwoWayTransformer", "install", "accelerate", "convert_encoder",
+           "convert_decoder", "convert_prompt_encoder"]
 
 
 def install(reference_modeling_module) -> None:
     """Class substitution: ``build_sam.py`` does ``from modeling import ImageEncoderViT, MaskDecoder, ...`` at import
     time (build_sam.py:11), so replacing the names on the package before that import swaps the path in."""
-    for cls in (ImageEncoderViT, MaskDecoder, TwoWayTransformer):
+    for cls in (ImageEncoderViT, MaskDecoder, TwoWayTransformer, PromptEncoder):
         setattr(reference_modeling_module, cls.__name__, cls)
 
 
@@ -56,6 +57,15 @@ def convert_decoder(ref: nn.Module) -> MaskDecoder:
     return new.to(device=p.device, dtype=p.dtype).train(ref.training)
 
 
+def convert_prompt_encoder(ref: nn.Module) -> PromptEncoder:
+    """Build the CUDA-path prompt encoder from a reference ``PromptEncoder`` instance."""
+    new = PromptEncoder(embed_dim=ref.embed_dim, image_embedding_size=tuple(ref.image_embedding_size),
+                        input_image_size=tuple(ref.input_image_size), mask_in_chans=ref.mask_downscaling[3].out_channels)
+    new.load_state_dict(ref.state_dict(), strict=True)
+    p = next(ref.parameters())
+    return new.to(device=p.device, dtype=p.dtype).train(ref.training)
+
+
 def accelerate(model: nn.Module) -> nn.Module:
     """Post-hoc module replacement on a built model.  Handles the reference's ``Sam`` (attributes ``image_encoder`` /
     ``mask_decoder``, sam.py:43-45) and uLLSAM's ``InternVLSAMModel`` (``vision_model`` / ``mask_decoder``,
@@ -66,4 +76,6 @@ def accelerate(model: nn.Module) -> nn.Module:
                 setattr(model, attr, convert_encoder(getattr(model, attr)))
         if hasattr(model, "mask_decoder") and not isinstance(model.mask_decoder, MaskDecoder):
             model.mask_decoder = convert_decoder(model.mask_decoder)
+        if hasattr(model, "prompt_encoder") and not isinstance(model.prompt_encoder, PromptEncoder):
+            model.prompt_encoder = convert_prompt_encoder(model.prompt_encoder)
     return model

@@ -142,3 +142,52 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     check(_lib.load().ullsam_op_cast_bf16(ptr(x), x.numel(), ptr(y), current_stream_ptr(x.device)),
           what="ullsam_op_cast_bf16")
     return y
+
+
+# ---- PromptEncoder (the step upstream of the decoder) ---------------------------------------------------------------
+
+def prompt_dense_pe(gauss: torch.Tensor, grid: int) -> torch.Tensor:
+    """PositionEmbeddingRandom.forward((grid, grid)) (prompt_encoder.py:230-241): gauss [2, F] -> [2F, grid, grid]."""
+    _require_cuda(gauss)
+    g = gauss.float().contiguous()
+    F = g.shape[1]
+    out = torch.empty((2 * F, grid, grid), dtype=torch.float32, device=g.device)
+    check(_lib.load().ullsam_op_prompt_dense_pe(ptr(g), F, grid, ptr(out), current_stream_ptr(g.device)),
+          what="ullsam_op_prompt_dense_pe")
+    return out
+
+
+def prompt_sparse(gauss: torch.Tensor, point_emb: torch.Tensor, not_a_point: torch.Tensor,
+                  coords: Optional[torch.Tensor], labels: Optional[torch.Tensor], boxes: Optional[torch.Tensor],
+                  pad: bool, img_w: float, img_h: float) -> torch.Tensor:
+    """_embed_points / _embed_boxes (prompt_encoder.py:76-103): -> [P, Ns, 2F] fp32."""
+    _require_cuda(gauss, point_emb, not_a_point, coords, labels, boxes)
+    g = gauss.float().contiguous()
+    F = g.shape[1]
+    pe, nap = point_emb.float().contiguous(), not_a_point.float().contiguous()
+    P = coords.shape[0] if coords is not None else boxes.shape[0]
+    Np = coords.shape[1] if coords is not None else 0
+    c = coords.float().contiguous() if coords is not None else None
+    l = labels.float().contiguous() if labels is not None else None
+    b = boxes.float().reshape(P, 4).contiguous() if boxes is not None else None
+    Ns = (Np + int(pad) if coords is not None else 0) + (2 if boxes is not None else 0)
+    out = torch.empty((P, Ns, 2 * F), dtype=torch.float32, device=g.device)
+    check(_lib.load().ullsam_op_prompt_sparse(ptr(g), F, ptr(pe), ptr(nap), ptr(c), ptr(l), P, Np, int(pad), ptr(b),
+                                              float(img_w), float(img_h), ptr(out), current_stream_ptr(g.device)),
+          what="ullsam_op_prompt_sparse")
+    return out
+
+
+def prompt_llm_dense(x: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """_normalize_llm_hidden_states (prompt_encoder.py:131-151): x [P, C, H, W] fp32/bf16 -> fp32, same shape."""
+    _require_cuda(x, scale, bias)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.contiguous()
+    P, Cc, H, W = x.shape
+    dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}[x.dtype]
+    out = torch.empty((P, Cc, H, W), dtype=torch.float32, device=x.device)
+    check(_lib.load().ullsam_op_prompt_llm_dense(ptr(x), dt, P, Cc, H * W, ptr(scale.float().contiguous()),
+                                                 ptr(bias.float().contiguous()), ptr(out), current_stream_ptr(x.device)),
+          what="ullsam_op_prompt_llm_dense")
+    return out
