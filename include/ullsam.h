@@ -207,6 +207,21 @@ int ullsam_op_prompt_sparse(const float* gauss, int F, const float* point_emb, c
 int ullsam_op_prompt_llm_dense(const void* x, int dtype, int P, int C, int HW, const float* scale, const float* bias,
                                float* out, void* stream);
 
+/* ---- mask post-processing (the step downstream of the decoder) ---------------------- */
+
+/* F.interpolate(x[..., :crop_h, :crop_w], (out_h, out_w), mode="bilinear", align_corners=False) on n = B*C fp32 planes of
+ * in_h x in_w, fused with the binarisation `> threshold` (Sam.mask_threshold = 0.0 on logits, sam.py:19,123 ==
+ * sigmoid > 0.5, app.py:644).  One call is uLLSAM's upsampling to the model size (train_joint_v2.py:1073-1079,
+ * app.py:635-641); two calls (-> img_size, then crop = input_size -> original_size) are Sam.postprocess_masks
+ * (sam.py:133-162).  out_f32 (fp32 logits) and out_u8 (0/1 bytes) are optional, at least one must be given. */
+int ullsam_op_resize_masks(const float* x, int n, int in_h, int in_w, int crop_h, int crop_w, int out_h, int out_w,
+                           float threshold, float* out_f32, unsigned char* out_u8, void* stream);
+
+/* CalcIoU (train_joint_v2.py:666-696): iou[i] = (|P & T| + smooth) / (|P | T| + smooth) with P = logits > threshold,
+ * T = target > 0.5, over n planes of hw elements (fp32). */
+int ullsam_op_mask_iou(const float* logits, const float* target, int n, size_t hw, float threshold, float smooth, float* iou,
+                       void* stream);
+
 /* fp32 -> bf16 (count elements). */
 int ullsam_op_cast_bf16(const float* x, size_t count, void* y_bf16, void* stream);
 

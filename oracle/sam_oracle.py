@@ -338,3 +338,27 @@ def segment(sd: SD, images: torch.Tensor, sparse: torch.Tensor, dense: torch.Ten
         masks.append(m)
         ious.append(s)
     return emb, torch.cat(masks), torch.cat(ious)
+
+
+# =====================================================================================================
+# post-processing (downstream of the decoder; reference modeling/sam.py, train_joint_v2.py)
+# =====================================================================================================
+def postprocess_masks(masks: torch.Tensor, input_size, original_size, img_size: int = 1024) -> torch.Tensor:
+    """Sam.postprocess_masks, sam.py:133-162."""
+    m = F.interpolate(masks, (img_size, img_size), mode="bilinear", align_corners=False)
+    m = m[..., : input_size[0], : input_size[1]]
+    return F.interpolate(m, tuple(original_size), mode="bilinear", align_corners=False)
+
+
+def upsample_masks(masks: torch.Tensor, img_size: int = 1024) -> torch.Tensor:
+    """uLLSAM's upsampling of the low-resolution logits to the model size (train_joint_v2.py:1073-1079, app.py:635-641)."""
+    return F.interpolate(masks, (img_size, img_size), mode="bilinear", align_corners=False)
+
+
+def calc_iou(logits: torch.Tensor, targets: torch.Tensor, smooth: float = 1e-7) -> torch.Tensor:
+    """CalcIoU.forward, train_joint_v2.py:666-696: [B, N, H, W] x2 -> [B, N]."""
+    p = (logits.sigmoid() > 0.5).float().flatten(2)
+    t = targets.flatten(2)
+    inter = (p * t).sum(-1)
+    union = p.sum(-1) + t.sum(-1) - inter
+    return (inter + smooth) / (union + smooth)

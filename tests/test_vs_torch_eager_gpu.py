@@ -62,3 +62,22 @@ def test_cuda_path_vs_pytorch_eager_bf16_on_this_gpu():
           f"speed-up {ms_eager / ms_ours:.1f}x, embeddings differ by rel-L2 {rel:.2e}")
     assert ms_ours < ms_eager
     assert rel < 3e-2   # two reduced-precision paths against each other (each is within 1e-2 of fp32)
+
+
+def test_fused_postprocess_vs_pytorch_eager_on_this_gpu():
+    """Downstream step: 32 masks 256^2 -> binary 1024^2, fused kernel vs F.interpolate + threshold."""
+    from ullsam_b200 import postprocess as PP
+
+    low = torch.randn(32, 1, 256, 256, device="cuda")
+
+    def eager():
+        return torch.nn.functional.interpolate(low, (1024, 1024), mode="bilinear", align_corners=False) > 0
+
+    def ours():
+        return PP.resize_masks(low, (1024, 1024), threshold=0.0, return_logits=False)[1]
+
+    ms_e, ms_o = _time(eager, 20), _time(ours, 20)
+    same = (eager() == ours().bool()).float().mean().item()
+    print(f"post-processing of 32 masks: PyTorch eager {ms_e * 1e3:.0f} us, fused kernel {ms_o * 1e3:.0f} us "
+          f"({ms_e / ms_o:.1f}x), identical pixels {same:.6f}")
+    assert same > 0.99999

@@ -129,6 +129,11 @@ PROTOTYPES = {
     ),
     "ullsam_op_im2col": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ullsam_op_cast_bf16": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "ullsam_op_resize_masks": (
+        C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                  C.c_void_p]),
+    "ullsam_op_mask_iou": (
+        C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "ullsam_op_prompt_dense_pe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ullsam_op_prompt_sparse": (
         C.c_int,

@@ -7,6 +7,7 @@
 #include "api_internal.h"
 #include "attention.h"
 #include "elementwise.h"
+#include "postprocess.h"
 #include "prompt.h"
 #include "gemm.h"
 
@@ -106,6 +107,21 @@ int ullsam_op_prompt_llm_dense(const void* x, int dtype, int P, int C, int HW, c
   if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_prompt_llm_dense: no sm_100 device");
   if (dtype != ULLSAM_F32 && dtype != ULLSAM_BF16) return op_fail(ULLSAM_ERR_INVALID, "op_prompt_llm_dense: dtype must be f32 or bf16");
   const char* e = launch_prompt_llm_dense(x, dtype == ULLSAM_BF16, P, C, HW, scale, bias, out, static_cast<cudaStream_t>(stream));
+  return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
+}
+
+int ullsam_op_resize_masks(const float* x, int n, int in_h, int in_w, int crop_h, int crop_w, int out_h, int out_w,
+                           float threshold, float* out_f32, unsigned char* out_u8, void* stream) {
+  if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_resize_masks: no sm_100 device");
+  const char* e = launch_resize_masks(x, n, in_h, in_w, crop_h, crop_w, out_h, out_w, threshold, out_f32, out_u8,
+                                      static_cast<cudaStream_t>(stream));
+  return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
+}
+
+int ullsam_op_mask_iou(const float* logits, const float* target, int n, size_t hw, float threshold, float smooth, float* iou,
+                       void* stream) {
+  if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_mask_iou: no sm_100 device");
+  const char* e = launch_mask_iou(logits, target, n, hw, threshold, smooth, iou, static_cast<cudaStream_t>(stream));
   return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
 }
 
