@@ -188,6 +188,14 @@ int ullsam_op_attention(const void* q, const void* k, const void* v, const void*
 /* PatchEmbed's im2col (image_encoder.py:387-395): images [B,3,1024,1024] (dtype) -> bf16 [B*4096, 768]. */
 int ullsam_op_im2col(const void* images, int dtype, int B, void* patches_bf16, void* stream);
 
+/* ---- MLLM bridge (InternVL pixel shuffle either side of the LLM) ------------------- */
+
+/* InternVLSAMModel.pixel_shuffle with downsample_ratio 0.5 as used by extract_feature (modeling_internvl_sam.py:211-251)
+ * and its inverse at the end of text_aware_dense_feature (:253-270):
+ *   to_tokens = 1: emb fp32 [B,256,64,64] -> tokens fp32 [B,1024,1024];  to_tokens = 0: the inverse.
+ * v1 = 1 reproduces ps_version 'v1' (height / width left swapped in the token order). */
+int ullsam_op_pixel_shuffle(const float* in, int B, int v1, int to_tokens, float* out, void* stream);
+
 /* ---- PromptEncoder on the device (the step upstream of the decoder) ---------------- */
 
 /* PositionEmbeddingRandom.forward == PromptEncoder.get_dense_pe without the batch dim (prompt_encoder.py:65-74, 230-241):

@@ -362,3 +362,46 @@ def calc_iou(logits: torch.Tensor, targets: torch.Tensor, smooth: float = 1e-7) 
     inter = (p * t).sum(-1)
     union = p.sum(-1) + t.sum(-1) - inter
     return (inter + smooth) / (union + smooth)
+
+
+# =====================================================================================================
+# MLLM bridge (either side of the language model; reference modeling/modeling_internvl_sam.py)
+# =====================================================================================================
+def pixel_shuffle(x: torch.Tensor, scale_factor: float = 0.5, ps_version: str = "v2") -> torch.Tensor:
+    """InternVLSAMModel.pixel_shuffle, modeling_internvl_sam.py:211-227 (x is NHWC)."""
+    n, h, w, c = x.size()
+    x = x.reshape(n, h, int(w * scale_factor), int(c / scale_factor))
+    x = x.permute(0, 2, 1, 3).contiguous()
+    x = x.reshape(n, int(w * scale_factor), int(h * scale_factor), int(c / (scale_factor * scale_factor)))
+    if ps_version != "v1":
+        x = x.permute(0, 2, 1, 3).contiguous()
+    return x
+
+
+def _projector(x: torch.Tensor, p: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """Sequential(LayerNorm, Linear, GELU, Linear), modeling_internvl_sam.py:88-101 (LayerNorm eps default 1e-5)."""
+    x = F.layer_norm(x, (x.shape[-1],), p["0.weight"], p["0.bias"], 1e-5)
+    x = F.gelu(F.linear(x, p["1.weight"], p["1.bias"]))
+    return F.linear(x, p["3.weight"], p["3.bias"])
+
+
+def mllm_extract_feature(vit_features: torch.Tensor, mlp1: Dict[str, torch.Tensor], ps_version: str = "v2") -> torch.Tensor:
+    """extract_feature after the encoder, modeling_internvl_sam.py:241-251: [B,256,64,64] -> [B,1024,H]."""
+    f = pixel_shuffle(vit_features.permute(0, 2, 3, 1), 0.5, ps_version)
+    f = f.reshape(f.shape[0], -1, f.shape[-1])
+    return _projector(f, mlp1)
+
+
+def text_aware_dense_feature(features: torch.Tensor, mlp2: Dict[str, torch.Tensor], ps_version: str = "v2",
+                             ratio: float = 0.5) -> torch.Tensor:
+    """modeling_internvl_sam.py:253-270: [B,1024,H] -> [B,256,64,64]."""
+    f = _projector(features, mlp2)
+    s = int(math.sqrt(f.shape[1]))
+    f = f.reshape(f.shape[0], s, s, f.shape[2])
+    if ps_version != "v1":
+        f = f.permute(0, 2, 1, 3).contiguous()
+    n, h, w, c = f.size()
+    f = f.reshape(n, h, int(w / ratio), int(c * ratio))
+    f = f.permute(0, 2, 1, 3).contiguous()
+    f = f.reshape(n, int(w / ratio), int(h / ratio), int(c * (ratio * ratio)))
+    return f.permute(0, 3, 1, 2).contiguous()

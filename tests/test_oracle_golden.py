@@ -100,3 +100,45 @@ def test_rel_pos_table_indexing():
     rp = torch.arange(27, dtype=torch.float32)[:, None].expand(27, 4)
     R = O.rel_pos_table(14, rp)
     assert R[0, 0, 0] == 13 and R[13, 0, 0] == 26 and R[0, 13, 0] == 0
+
+
+def test_bridge_restatement_vs_reference_golden():
+    """oracle pixel_shuffle / mllm_extract_feature / text_aware_dense_feature against outputs of the reference's own
+    InternVLSAMModel methods (oracle/make_golden_bridge.py)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import sam_oracle as O
+    from oracle.make_golden_bridge import make_mlp
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bridge.npz"))
+    H = int(g["H"])
+    emb = torch.randn(1, 256, 64, 64, generator=torch.Generator().manual_seed(11))
+    hid = torch.randn(1, 1024, H, generator=torch.Generator().manual_seed(12))
+    p1 = {k: v.detach() for k, v in make_mlp(1024, H, H, 21).state_dict().items()}
+    p2 = {k: v.detach() for k, v in make_mlp(H, 1024, 1024, 22).state_dict().items()}
+    with torch.no_grad():
+        for v in ("v2", "v1"):
+            assert np.array_equal(O.pixel_shuffle(emb.permute(0, 2, 3, 1), 0.5, v)[:, ::4, ::4, ::8].numpy(), g[f"shuffle_{v}"])
+            tok = O.mllm_extract_feature(emb, p1, v)
+            assert np.abs(tok[:, ::16].numpy() - g[f"tokens_{v}"]).max() < 1e-5
+            dense = O.text_aware_dense_feature(hid, p2, v)
+            assert np.abs(dense[:, :, ::4, ::4].numpy() - g[f"dense_{v}"]).max() < 1e-5
+
+
+def test_postprocess_restatement_vs_reference_golden():
+    """oracle postprocess_masks / calc_iou against the reference's Sam.postprocess_masks and CalcIoU
+    (oracle/make_golden_post.py)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import sam_oracle as O
+    from oracle.make_golden_post import CASES, low_res
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "post.npz"))
+    for i, (inp, orig) in enumerate(CASES):
+        m = O.postprocess_masks(low_res(30 + i), inp, orig)
+        assert np.array_equal(m[:, :, ::13, ::13].numpy(), g[f"post_{i}"])
+    logits = torch.nn.functional.interpolate(low_res(40), (512, 512), mode="bilinear", align_corners=False)
+    target = (torch.nn.functional.interpolate(low_res(41), (512, 512), mode="bilinear", align_corners=False) > 0.5).float()
+    assert np.allclose(O.calc_iou(logits, target).numpy(), g["iou"], atol=1e-7)

@@ -110,6 +110,12 @@ int ullsam_op_prompt_llm_dense(const void* x, int dtype, int P, int C, int HW, c
   return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
 }
 
+int ullsam_op_pixel_shuffle(const float* in, int B, int v1, int to_tokens, float* out, void* stream) {
+  if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_pixel_shuffle: no sm_100 device");
+  const char* e = launch_pixel_shuffle(in, B, v1, to_tokens, out, static_cast<cudaStream_t>(stream));
+  return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
+}
+
 int ullsam_op_resize_masks(const float* x, int n, int in_h, int in_w, int crop_h, int crop_w, int out_h, int out_w,
                            float threshold, float* out_f32, unsigned char* out_u8, void* stream) {
   if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_resize_masks: no sm_100 device");

@@ -83,8 +83,46 @@ const char* launch_layernorm(const float* x, const float* gamma, const float* be
     case 768: layernorm_kernel<6><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, eps, grid, window, rows_out, y); break;
     case 1024: layernorm_kernel<8><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, eps, grid, window, rows_out, y); break;
     case 1280: layernorm_kernel<10><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, eps, grid, window, rows_out, y); break;
-    default: return "layernorm: dim must be 256, 768, 1024 or 1280";
+    case 2048: layernorm_kernel<16><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, eps, grid, window, rows_out, y); break;
+    default: return "layernorm: dim must be 256, 768, 1024, 1280 or 2048";
   }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// InternVL pixel shuffle between the SAM embedding and the LLM tokens (modeling_internvl_sam.py:211-270,
+// downsample_ratio 0.5): tokens[b][(y/2)*32 + x/2][(y%2)*512 + (x%2)*256 + c] <-> emb[b][c][y][x] for ps_version 'v2';
+// 'v1' leaves height and width swapped in the token order ((x/2)*32 + y/2).  to_tokens = 1: NCHW -> tokens (the
+// gather of extract_feature), 0: tokens -> NCHW (the scatter at the end of text_aware_dense_feature).
+// One thread per element of the DESTINATION, fastest index contiguous there; 4 MB per image, L2-served.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restrict__ in, int B, int v1, int to_tokens,
+                                                            float* __restrict__ out) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(B) * 256 * 4096;
+  if (idx >= total) return;
+  const int b = static_cast<int>(idx >> 20);
+  const int r = static_cast<int>(idx & ((1u << 20) - 1));
+  if (to_tokens) {
+    const int tok = r >> 10, f = r & 1023;
+    const int a = tok >> 5, bb = tok & 31;            // v2: a = y/2, bb = x/2; v1: a = x/2, bb = y/2
+    const int yh = v1 ? bb : a, xh = v1 ? a : bb;
+    const int y = 2 * yh + (f >> 9), x = 2 * xh + ((f >> 8) & 1), c = f & 255;
+    out[idx] = in[(static_cast<size_t>(b) * 256 + c) * 4096 + y * 64 + x];
+  } else {
+    const int c = r >> 12, y = (r >> 6) & 63, x = r & 63;
+    const int yh = y >> 1, xh = x >> 1;
+    const int tok = v1 ? (xh * 32 + yh) : (yh * 32 + xh);
+    const int f = (y & 1) * 512 + (x & 1) * 256 + c;
+    out[idx] = in[(static_cast<size_t>(b) * 1024 + tok) * 1024 + f];
+  }
+}
+
+const char* launch_pixel_shuffle(const float* in, int B, int v1, int to_tokens, float* out, cudaStream_t stream) {
+  if (B <= 0) return nullptr;
+  const size_t total = static_cast<size_t>(B) * 256 * 4096;
+  pixel_shuffle_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(in, B, v1, to_tokens, out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

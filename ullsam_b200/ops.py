@@ -191,3 +191,22 @@ def prompt_llm_dense(x: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor) -
                                                  ptr(bias.float().contiguous()), ptr(out), current_stream_ptr(x.device)),
           what="ullsam_op_prompt_llm_dense")
     return out
+
+
+# ---- MLLM bridge ------------------------------------------------------------------------------------------------------
+
+def pixel_shuffle(x: torch.Tensor, to_tokens: bool, ps_version: str = "v2") -> torch.Tensor:
+    """InternVL pixel shuffle with ratio 0.5 (modeling_internvl_sam.py:211-270): emb fp32 [B,256,64,64] -> tokens
+    [B,1024,1024] (``to_tokens``) or back."""
+    _require_cuda(x)
+    x = x.float().contiguous()
+    B = x.shape[0]
+    if to_tokens:
+        assert x.shape[1:] == (256, 64, 64)
+        out = torch.empty((B, 1024, 1024), dtype=torch.float32, device=x.device)
+    else:
+        assert x.shape[1:] == (1024, 1024)
+        out = torch.empty((B, 256, 64, 64), dtype=torch.float32, device=x.device)
+    check(_lib.load().ullsam_op_pixel_shuffle(ptr(x), B, int(ps_version == "v1"), int(to_tokens), ptr(out),
+                                              current_stream_ptr(x.device)), what="ullsam_op_pixel_shuffle")
+    return out
