@@ -113,6 +113,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def workload_config(model: str, B: int, world: int) -> dict:
+    """The `config` object of the JSON line (shared by the CUDA arm and the reference arm)."""
+    return {"workload": f"SAM {model} image encoder + mask decoder, batch {B} of 1024x1024 per GPU, 1 box-shaped "
+                        "prompt per image, random-init weights (configs[1] of BASELINE.json)",
+            "images_per_gpu_per_step": B, "global_batch": world * B,
+            "parallelism": f"dp{world} (batch-sharded, weights replicated)",
+            "collective": "all_gather(mask logits, iou) per step" if world > 1 else "none",
+            "l2": "inputs (403 MB of images per step) and activations exceed the 126 MB L2; no flush needed",
+            "residual_stream": "fp32", "gemm_operands": "bf16", "accumulate": "fp32"}
+
+
 def run_reference(args):
     """The reference's CPU implementation of the path (oracle port), all host threads, one image per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -148,9 +159,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"SAM {args.model} image encoder + mask decoder, 1024x1024, 1 box-shaped prompt per image, "
-                               "random-init weights — the reference's CPU path (oracle port, fp32), bounded sample of 1 image per step",
-                   "images_per_step": 1},
+        # the same workload as the CUDA arm (its `config`); a step here is a bounded sample of it: ONE image + prompt
+        "config": dict(workload_config(args.model, args.batch, args.gpus),
+                       reference_arm="the reference's CPU path (fp32 oracle port of its PyTorch modules, all host threads); "
+                                     "each step is a bounded sample of the workload: 1 image + 1 prompt"),
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -358,12 +370,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "images/s", "per_gpu": value / world, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"SAM {args.model} image encoder + mask decoder, batch {B} of 1024x1024 per GPU, 1 box-shaped "
-                                   "prompt per image, random-init weights (configs[1] of BASELINE.json)",
-                       "images_per_gpu_per_step": B, "global_batch": world * B, "parallelism": f"dp{world} (batch-sharded, weights replicated)",
-                       "collective": "all_gather(mask logits, iou) per step" if world > 1 else "none",
-                       "l2": "inputs (403 MB of images per step) and activations exceed the 126 MB L2; no flush needed",
-                       "residual_stream": "fp32", "gemm_operands": "bf16", "accumulate": "fp32"},
+            "config": workload_config(args.model, B, world),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }))
     if world > 1:
