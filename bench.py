@@ -344,6 +344,15 @@ def main():
                  "frac_of_burst": value / world * fl["total"] / 1e12 / peaks["bf16_burst"], "flops_per_image": fl["total"]},
         "kernels": kernels,
     }
+    # the single kernel symbol with the largest share of the step (profiles/r1g_launches.csv) is the fused global
+    # attention, MUFU-co-bound (softmax of d = 64 heads); reported next to the GEMM family so neither hides the other
+    ag = kernels.get("attn_global")
+    if ag and ag.get("tflops"):
+        roofline["largest_single_kernel"] = {
+            "kernel": "attention_kernel<64> (fused global attention with decomposed rel-pos bias)",
+            "share_of_step": ag["ms_per_step"] / (ms_total / args.steps), "achieved": ag["tflops"], "unit": "TFLOP/s",
+            "frac": ag["tflops"] / peaks["bf16_sustained"], "ms_per_launch": ag["ms_per_step"] / max(ag["launches_per_step"], 1e-9),
+            "note": "exp2 on the MUFU pipe bounds it near 50 % tensor utilisation (DESIGN.md section 4)"}
 
     # ------------------------------------------------------------------ CPU baseline (oracle port), rank 0 at N == 1 only
     cpu = None
