@@ -97,15 +97,26 @@ ULLSAM_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
+// Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) after ~4 s of wall time instead of a hung
+// GPU.  The clock is only read once the wait has already failed 256 times, so the normal path costs nothing.
+ULLSAM_DEVICE uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 ULLSAM_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) {
-      printf("ullsam: mbarrier timeout block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x,
-             blockIdx.y, threadIdx.x, smem_u32(bar), parity);
-      __trap();
+    if ((++spins & 255u) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) {
+        printf("ullsam: mbarrier timeout block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y, threadIdx.x,
+               smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }
