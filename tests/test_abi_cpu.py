@@ -143,3 +143,35 @@ def test_bench_flop_model_matches_baseline_md():
     assert abs(f["attn_global"] / 4e9 - (51.54 + 0.81)) < 0.3
     fl = bench.flops_per_image(config("vit_l"))
     assert abs(fl["total"] / 1e9 - 2840.6) < 4.0
+
+
+def test_prompt_encoder_shim_keeps_the_reference_state_dict_and_is_loud_on_cpu():
+    """SURVEY App. B prompt_encoder.* keys; no CPU path (the shim raises instead of computing anything on the host)."""
+    from ullsam_b200 import _lib
+    from ullsam_b200.modeling import PromptEncoder
+
+    pe = PromptEncoder(embed_dim=256, image_embedding_size=(64, 64), input_image_size=(1024, 1024), mask_in_chans=16)
+    keys = set(pe.state_dict())
+    expect = {"pe_layer.positional_encoding_gaussian_matrix", "not_a_point_embed.weight", "no_mask_embed.weight",
+              "llm_scale_factor", "llm_bias"}
+    expect |= {f"point_embeddings.{i}.weight" for i in range(4)}
+    expect |= {f"mask_downscaling.{i}.{p}" for i in (0, 1, 3, 4, 6) for p in ("weight", "bias")}
+    assert keys == expect
+    assert pe.state_dict()["pe_layer.positional_encoding_gaussian_matrix"].shape == (2, 128)
+    assert float(pe.llm_scale_factor) == pytest.approx(0.1) and float(pe.llm_bias) == 0.0   # prompt_encoder.py:51-52
+    with pytest.raises(_lib.UllsamError):
+        pe.get_dense_pe()
+    with pytest.raises(_lib.UllsamError):
+        pe(points=None, boxes=torch.zeros(1, 4), masks=None)
+
+
+def test_postprocess_and_bridge_are_loud_on_cpu():
+    from ullsam_b200 import _lib, bridge, postprocess
+
+    with pytest.raises(_lib.UllsamError):
+        postprocess.resize_masks(torch.zeros(1, 1, 256, 256), (1024, 1024))
+    with pytest.raises(_lib.UllsamError):
+        postprocess.mask_iou(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8))
+    mlp = torch.nn.Sequential(torch.nn.LayerNorm(1024), torch.nn.Linear(1024, 64), torch.nn.GELU(), torch.nn.Linear(64, 64))
+    with pytest.raises(_lib.UllsamError):
+        bridge.extract_feature(lambda x: x, mlp, torch.zeros(1, 256, 64, 64))
