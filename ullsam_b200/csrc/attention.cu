@@ -28,6 +28,8 @@
 // (global: rel_w fp32 in [kw/4][row][4] order for conflict-free 16-byte reads, rel_h as halves) or keeps them
 // in registers (windowed).
 #include "attention.h"
+
+#include <stdlib.h>
 // 1: global attention with ONE thread per query row (8 softmax warps, row-max bound instead of an exchange);
 // 0: the two-threads-per-row layout that the windowed kernel uses.
 // 1: (debug builds only, tools/build_variant.sh) print a per-phase cycle breakdown of two softmax warps of CTA (0,0)
@@ -846,6 +848,9 @@ const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, con
   if (grid == 64) return launch_t<64>(q, k, v, rel_h, rel_w, G, heads, out, stream);
   if (grid == 14) {
     if (G % 25 != 0) return "attention: windowed mode needs 25 windows per image";
+    // default: the four-query-tiles-per-SM design (attention_win.cu); ULLSAM_WIN_ATT=1 selects the first design
+    static const int win_ver = getenv("ULLSAM_WIN_ATT") ? atoi(getenv("ULLSAM_WIN_ATT")) : 2;
+    if (win_ver == 2) return launch_attention_windowed_v2(q, k, v, rel_h, rel_w, G, heads, out, stream);
     return launch_t<14>(q, k, v, rel_h, rel_w, G, heads, out, stream);
   }
   return "attention: grid must be 64 (global) or 14 (windowed)";

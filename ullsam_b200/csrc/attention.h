@@ -14,4 +14,9 @@ namespace ullsam {
 const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
                              const __nv_bfloat16* rel_h, const __nv_bfloat16* rel_w, int G, int heads, int grid, __nv_bfloat16* out, cudaStream_t stream);
 
+// second windowed design (attention_win.cu): one CTA per (window, head), both query tiles, 4 key tiles of 49
+const char* launch_attention_windowed_v2(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                                         const __nv_bfloat16* rel_h, const __nv_bfloat16* rel_w, int G, int heads,
+                                         __nv_bfloat16* out, cudaStream_t stream);
+
 }  // namespace ullsam
