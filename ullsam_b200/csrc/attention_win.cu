@@ -8,19 +8,33 @@
 // -> PV -> store) that keeps the MUFU and tensor pipes ~25 % / ~13 % busy.  Here a CTA owns BOTH query tiles of a
 // (window, head) at 128 columns each, so FOUR query tiles are in flight per SM and K / V / the bias tables are loaded
 // once per window instead of twice:
-//   * 4 key tiles of 49 keys (3.5 key-grid rows; MMA N = 64, 15 columns masked) through ONE 64-column S slot per query
-//     tile; P is written back over it as packed bf16 (32 columns); O accumulates in the other 64 columns (which hold
-//     the Q.R^T bias tables until the gather has consumed them);
-//   * one softmax thread per query row (thread == TMEM lane, no cross-thread exchange): pass A folds the raw row
-//     maximum into an upper bound of the biased scores, pass B re-reads the scores in 16-column pieces, adds the bias,
-//     exponentiates, and stores P (same scheme as the global kernel, attention.cu);
-//   * everything is resident in shared memory (Q 32 KB, K 32 KB, V 32 KB), every mbarrier is used exactly once (no
-//     rings, no phase bookkeeping): 34 barriers.
-// CTA = 10 warps: 8 softmax (2 query tiles x 4 lane quadrants), 1 TMA producer, 1 MMA issuer; 2 CTAs / SM.
+//   * 7 key tiles of 28 keys = two key-grid rows each (MMA N = 32, 4 columns masked) through TWO 32-column S slots per
+//     query tile, so QK(t+1) is computed while the softmax of tile t runs; P is written back over its slot as packed
+//     bf16 (16 columns); O accumulates in the upper 64 columns (which hold the Q.R^T bias tables until the gather has
+//     consumed them);
+//   * one softmax thread per query row (thread == TMEM lane, no cross-thread exchange); the 32 scores of a tile are
+//     read once and stay in registers for the bias add, the exact row maximum and the exponentials;
+//   * everything is resident in shared memory (Q 32 KB, K 28 KB, V 28 KB), every mbarrier is used exactly once (no
+//     rings, no phase bookkeeping).
+// CTA = 10 warps: 8 softmax (2 query tiles x 4 lane quadrants) and 2 control warps, each the MMA issuer of one query tile
+// (so the two tiles' QK -> softmax -> PV chains do not wait for each other; one of them also issues the TMA loads);
+// 2 CTAs / SM.
 #include "attention.h"
+
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.h"
+
+#ifndef ULLSAM_WIN_TIMELINE
+#define ULLSAM_WIN_TIMELINE 0
+#endif
+#if ULLSAM_WIN_TIMELINE
+#define WTL(i) do { const long long t_ = clock64(); wtl[i] += t_ - wtl_last; wtl_last = t_; } while (0)
+#else
+#define WTL(i) do { } while (0)
+#endif
 
 namespace ullsam {
 namespace {
@@ -29,20 +43,24 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 struct W {
   static constexpr int GRID = 14, T = 196;
-  static constexpr int TK = 49;                        // keys per tile (4 tiles)
+  static constexpr int NT = 7, TK = 28, TN = 32;       // key tiles, keys per tile, MMA N (tile rows in shared memory)
+  static constexpr int TILE_BYTES = TN * 128;          // 4 KB
   static constexpr int NREL = 32;                      // padded rows of the rel-pos tables
-  static constexpr int THREADS = 320;
-  static constexpr int OFF_Q = 0;                      // 2 x [128 x 64] bf16
-  static constexpr int OFF_K = 32768;                  // 4 x [64 x 64] bf16
-  static constexpr int OFF_V = 65536;                  // 4 x [64 x 64] bf16
-  static constexpr int OFF_TABW = OFF_V + 3 * 8192;    // the two 4 KB tables ride in V tile 3's slot until the bias MMAs retire
-  static constexpr int OFF_TABH = OFF_TABW + 4096;
-  static constexpr int OFF_SCR = 98304;                // fp32 [14][256]: rel_h of every row (and the rel_w scatter before it)
+  static constexpr int THREADS = 320;                  // 8 softmax warps, 2 control warps (TMA + one MMA issuer each)
+  static constexpr int Q1_ROWS = 72;                   // query tile 1 has 68 valid rows: only 9 swizzle atoms are loaded; the
+                                                       // MMA's remaining A rows read on into the K tiles (finite, never stored)
+  static constexpr int OFF_Q = 0;                      // [128 x 64] + [72 x 64] bf16
+  static constexpr int OFF_K = 16384 + Q1_ROWS * 128;  // 7 x [32 x 64] bf16
+  static constexpr int OFF_V = OFF_K + NT * TILE_BYTES;
+  static constexpr int OFF_TABW = OFF_V + 5 * TILE_BYTES;   // the two 4 KB tables ride in V tiles 5 and 6 until the bias MMAs retire
+  static constexpr int OFF_TABH = OFF_V + 6 * TILE_BYTES;
+  static constexpr int OFF_SCR = OFF_V + NT * TILE_BYTES;   // fp32 [14][256]: rel_h of every row (and the rel_w scatter before it)
   static constexpr int OFF_BAR = OFF_SCR + 14 * 256 * 4;
-  static constexpr int NBAR = 2 + 4 + 4 + 8 + 8 + 8;
+  static constexpr int NBAR = 2 + 2 * NT + 3 * 2 * NT;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
-  static constexpr int TMEM_COLS = 256;                // per query tile: S/P [0,64), O (tables first) [64,128)
+  static constexpr int TMEM_COLS = 256;                // per query tile: S/P slots [0,32) [32,64), O (tables first) [64,128)
 };
+static_assert(W::OFF_K % 1024 == 0 && W::OFF_V % 1024 == 0 && W::OFF_SCR % 16 == 0, "swizzle atoms need 1024-byte alignment");
 
 ULLSAM_DEVICE float ex2(float x) {
   float y;
@@ -51,7 +69,8 @@ ULLSAM_DEVICE float ex2(float x) {
 }
 
 __global__ void __launch_bounds__(W::THREADS, 2)
-windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ1,
+                          const __grid_constant__ CUtensorMap tmK,
                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmRh,
                           const __grid_constant__ CUtensorMap tmRw, int heads, __nv_bfloat16* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
@@ -59,12 +78,13 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + W::OFF_BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* pro_done = bars + 1;
-  uint64_t* k_full = bars + 2;        // [4]
-  uint64_t* v_full = k_full + 4;      // [4]
-  uint64_t* s_full = v_full + 4;      // [qt][4]
-  uint64_t* p_ready = s_full + 8;     // [qt][4]
-  uint64_t* o_done = p_ready + 8;     // [qt][4]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 8);
+  constexpr int NT = W::NT;
+  uint64_t* k_full = bars + 2;         // [NT]
+  uint64_t* v_full = k_full + NT;      // [NT]
+  uint64_t* s_full = v_full + NT;      // [qt][NT]
+  uint64_t* p_ready = s_full + 2 * NT; // [qt][NT]
+  uint64_t* o_done = p_ready + 2 * NT; // [qt][NT]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2 * NT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gh = blockIdx.x;                       // window * heads + head
@@ -73,25 +93,25 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   if (warp == 8) {
     if (elect_one_sync()) {
       mbar_init(q_full, 1);
-      mbar_init(pro_done, 1);
-      for (int i = 0; i < 4; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); }
-      for (int i = 0; i < 8; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_done[i], 1); }
+      mbar_init(pro_done, 2);   // one commit per MMA warp
+      for (int i = 0; i < NT; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); }
+      for (int i = 0; i < 2 * NT; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_done[i], 1); }
       fence_barrier_init();
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-      mbar_arrive_expect_tx(q_full, 2 * 16384 + 2 * 4096);
+      mbar_arrive_expect_tx(q_full, 16384 + W::Q1_ROWS * 128 + 2 * 4096);
       tma_load_2d(smem + W::OFF_Q, &tmQ, q_full, 0, row_base);
-      tma_load_2d(smem + W::OFF_Q + 16384, &tmQ, q_full, 0, row_base + 128);
+      tma_load_2d(smem + W::OFF_Q + 16384, &tmQ1, q_full, 0, row_base + 128);
       tma_load_2d(smem + W::OFF_TABW, &tmRw, q_full, 0, 0);
       tma_load_2d(smem + W::OFF_TABH, &tmRh, q_full, 0, 0);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        mbar_arrive_expect_tx(&k_full[t], 8192);
-        tma_load_2d(smem + W::OFF_K + t * 8192, &tmK, &k_full[t], 0, row_base + t * W::TK);
+      for (int t = 0; t < NT; ++t) {
+        mbar_arrive_expect_tx(&k_full[t], W::TILE_BYTES);
+        tma_load_2d(smem + W::OFF_K + t * W::TILE_BYTES, &tmK, &k_full[t], 0, row_base + t * W::TK);
       }
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        mbar_arrive_expect_tx(&v_full[t], 8192);
-        tma_load_2d(smem + W::OFF_V + t * 8192, &tmV, &v_full[t], 0, row_base + t * W::TK);
+      for (int t = 0; t < 5; ++t) {
+        mbar_arrive_expect_tx(&v_full[t], W::TILE_BYTES);
+        tma_load_2d(smem + W::OFF_V + t * W::TILE_BYTES, &tmV, &v_full[t], 0, row_base + t * W::TK);
       }
     }
     __syncwarp();
@@ -105,69 +125,68 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 8) {
-    // ================================ TMA producer (rest): V tile 3 once its slot no longer holds the tables ==========
-    if (elect_one_sync()) {
-      mbar_wait(pro_done, 0);
-      mbar_arrive_expect_tx(&v_full[3], 8192);
-      tma_load_2d(smem + W::OFF_V + 3 * 8192, &tmV, &v_full[3], 0, row_base + 3 * W::TK);
-    }
-  } else if (warp == 9) {
-    // ================================ MMA issuer ======================================================================
+  if (warp == 8 || warp == 9) {
+    // ================================ MMA issuers: one warp per query tile (independent chains) ========================
     const bool leader = elect_one_sync();
-    constexpr uint32_t idesc_qk = make_idesc_bf16(128, 64, 0, 0);
+    const int qt = 9 - warp;   // warp 9 (TMEM owner): query tile 0; warp 8 (TMA producer): query tile 1
+    constexpr uint32_t idesc_qk = make_idesc_bf16(128, W::TN, 0, 0);
     constexpr uint32_t idesc_rel = make_idesc_bf16(128, W::NREL, 0, 0);
     constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);   // A = P (TMEM), B = V (smem, MN-major)
-    const uint32_t sq = smem_u32(smem + W::OFF_Q), sk = smem_u32(smem + W::OFF_K), sv = smem_u32(smem + W::OFF_V);
+    const uint32_t sq = smem_u32(smem + W::OFF_Q) + qt * 16384, sk = smem_u32(smem + W::OFF_K), sv = smem_u32(smem + W::OFF_V);
+    const uint32_t tq0 = tmem_base + qt * 128;
+    const uint64_t dq = make_smem_desc_sw128(sq, 16, 1024);
     mbar_wait(q_full, 0);
     tc_fence_after();
     if (leader) {
       const uint64_t drw = make_smem_desc_sw128(smem_u32(smem + W::OFF_TABW), 16, 1024);
       const uint64_t drh = make_smem_desc_sw128(smem_u32(smem + W::OFF_TABH), 16, 1024);
 #pragma unroll
-      for (int qt = 0; qt < 2; ++qt) {
-        const uint64_t dq = make_smem_desc_sw128(sq + qt * 16384, 16, 1024);
+      for (int k = 0; k < 4; ++k) umma_ss(tq0 + 64, dq + 2 * k, drw + 2 * k, idesc_rel, k != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + qt * 128 + 64, dq + 2 * k, drw + 2 * k, idesc_rel, k != 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + qt * 128 + 96, dq + 2 * k, drh + 2 * k, idesc_rel, k != 0);
-      }
+      for (int k = 0; k < 4; ++k) umma_ss(tq0 + 96, dq + 2 * k, drh + 2 * k, idesc_rel, k != 0);
       umma_commit(pro_done);
     }
     __syncwarp();
-    auto issue_qk = [&](int t, int qt) {   // S[qt] = Q[qt] K(t)^T
-      if (qt == 0) {
-        mbar_wait(&k_full[t], 0);
-        tc_fence_after();
-      }
-      const uint64_t dq = make_smem_desc_sw128(sq + qt * 16384, 16, 1024);
-      const uint64_t dk = make_smem_desc_sw128(sk + t * 8192, 16, 1024);
+    if (warp == 8) {
+      // V tiles 5, 6 share their slots with the tables: load them once BOTH warps' bias MMAs have retired
+      mbar_wait(pro_done, 0);
       if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + qt * 128, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
-        umma_commit(&s_full[qt * 4 + t]);
+        for (int t = 5; t < NT; ++t) {
+          mbar_arrive_expect_tx(&v_full[t], W::TILE_BYTES);
+          tma_load_2d(smem + W::OFF_V + t * W::TILE_BYTES, &tmV, &v_full[t], 0, row_base + t * W::TK);
+        }
+      }
+      __syncwarp();
+    }
+    auto issue_qk = [&](int t) {   // S[t & 1] = Q K(t)^T
+      mbar_wait(&k_full[t], 0);
+      tc_fence_after();
+      const uint64_t dk = make_smem_desc_sw128(sk + t * W::TILE_BYTES, 16, 1024);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tq0 + (t & 1) * 32, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[qt * NT + t]);
       }
       __syncwarp();
     };
-    issue_qk(0, 0);
-    issue_qk(0, 1);
+    issue_qk(0);
+    issue_qk(1);
 #pragma unroll 1
-    for (int t = 0; t < 4; ++t) {
-#pragma unroll 1
-      for (int qt = 0; qt < 2; ++qt) {
-        if (qt == 0) mbar_wait(&v_full[t], 0);
-        const uint64_t dv = make_smem_desc_sw128(sv + t * 8192, 16, 1024);
-        mbar_wait(&p_ready[qt * 4 + t], 0);   // P(t) of this query tile is in its slot (and, for t = 0, the tables are consumed)
-        tc_fence_after();
-        if (leader) {
+    for (int t = 0; t < NT; ++t) {
+      mbar_wait(&v_full[t], 0);
+      const uint64_t dv = make_smem_desc_sw128(sv + t * W::TILE_BYTES, 16, 1024);
+      mbar_wait(&p_ready[qt * NT + t], 0);   // P(t) is in its slot (and, for t = 0, the tables are consumed)
+      tc_fence_after();
+      if (leader) {
 #pragma unroll
-          for (int s2 = 0; s2 < 4; ++s2)
-            umma_ts(tmem_base + qt * 128 + 64, tmem_base + qt * 128 + s2 * 8, dv + s2 * 128, idesc_pv, (t | s2) != 0);
-          umma_commit(&o_done[qt * 4 + t]);
-        }
-        __syncwarp();
-        if (t + 1 < 4) issue_qk(t + 1, qt);   // tcgen05 ops of one thread execute in order: S(t+1) lands after PV(t) has read P(t)
+        for (int s2 = 0; s2 < 2; ++s2)
+          umma_ts(tq0 + 64, tq0 + (t & 1) * 32 + s2 * 8, dv + s2 * 128, idesc_pv, (t | s2) != 0);
+        umma_commit(&o_done[qt * NT + t]);
       }
+      __syncwarp();
+      // the slot of tile t is free once PV(t) has read P(t); tcgen05 ops of one thread execute in order
+      if (t + 2 < NT) issue_qk(t + 2);
     }
   } else {
     // ================================ softmax warps: one thread per query row ========================================
@@ -179,9 +198,15 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     float* scr = reinterpret_cast<float*>(smem + W::OFF_SCR);   // [14][256]
     const int col = qt * 128 + r;
 
+#if ULLSAM_WIN_TIMELINE
+    long long wtl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long wtl_last = clock64();
+    const long long wtl_begin = wtl_last;
+#endif
     // ---- bias rows: w[kw] = Tw[row][qw - kw + 13] (registers), h[kh] = Th[row][qh - kh + 13] (shared memory) ----
     mbar_wait(pro_done, 0);
     tc_fence_after();
+    WTL(0);
     float w[14];
     float wmax = -INFINITY;
     {
@@ -215,98 +240,87 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       __syncwarp();
     }
     tc_fence_before();
+    WTL(1);
 
     const float cs = 0.125f * kLog2e;
     float m_used = -INFINITY, l0 = 0.f, l1 = 0.f;
     const uint32_t o_addr = tbase + 64;
+    (void)wmax;
 
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      mbar_wait(&s_full[qt * 4 + t], 0);
+    for (int t = 0; t < NT; ++t) {
+      const float h0 = scr[(2 * t) * 256 + col], h1 = scr[(2 * t + 1) * 256 + col];   // key-grid rows 2t, 2t+1
+      mbar_wait(&s_full[qt * NT + t], 0);
       tc_fence_after();
-      // key c of this tile is key 49 t + c of the window: key-grid row (49 t + c) / 14, column (49 t + c) % 14
-      constexpr int kFirstRow[4] = {0, 3, 7, 10};      // (49 t) / 14
-      constexpr int kNumRows[4] = {4, 4, 4, 4};        // key-grid rows touched by the tile: 0-3, 3-6, 7-10, 10-13
-      float hrow[4];
-      float hmax = -INFINITY;
-#pragma unroll
-      for (int a = 0; a < kNumRows[t]; ++a) {
-        hrow[a] = scr[(kFirstRow[t] + a) * 256 + col];
-        hmax = fmaxf(hmax, hrow[a]);
-      }
-      // ---- pass A: raw maximum over the 49 valid columns ----
+      WTL(2);
+      const uint32_t s_addr = tbase + (t & 1) * 32;
+      uint32_t v[32];
+      tmem_ld32(s_addr, v);
+      tmem_wait_ld();
+      // ---- biased scores (log2 units) of the 28 keys of the tile and their exact maximum ----
+      float x[28];
       float mx0 = -INFINITY, mx1 = -INFINITY;
-      {
-        uint32_t a0[32], a1[16];
-        tmem_ld32(tbase, a0);
-        tmem_ld16(tbase + 32, a1);
-        const uint32_t a48 = tmem_ld1(tbase + 48);      // column 48 is the last valid one
-        tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) mx0 = fmax3(mx0, __uint_as_float(a0[i]), __uint_as_float(a0[i + 1]));
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) mx1 = fmax3(mx1, __uint_as_float(a1[i]), __uint_as_float(a1[i + 1]));
-        mx1 = fmaxf(mx1, __uint_as_float(a48));
+      for (int c = 0; c < 14; c += 2) {
+        x[c] = fmaf(__uint_as_float(v[c]), cs, h0) + w[c];
+        x[c + 1] = fmaf(__uint_as_float(v[c + 1]), cs, h0) + w[c + 1];
+        x[14 + c] = fmaf(__uint_as_float(v[14 + c]), cs, h1) + w[c];
+        x[15 + c] = fmaf(__uint_as_float(v[15 + c]), cs, h1) + w[c + 1];
+        mx0 = fmax3(mx0, x[c], x[c + 1]);
+        mx1 = fmax3(mx1, x[14 + c], x[15 + c]);
       }
-      const float mx = fmaf(fmaxf(mx0, mx1), cs, wmax + hmax);
+      const float mx = fmaxf(mx0, mx1);
+      WTL(3);
       const bool need = mx > m_used + 8.0f;
       if (__any_sync(0xffffffffu, need)) {
         const float alpha = need ? ex2(m_used - mx) : 1.0f;
         l0 *= alpha;
         l1 *= alpha;
         if (t > 0) {
-          mbar_wait(&o_done[qt * 4 + t - 1], 0);       // PV(t-1) retired: O is quiescent
+          mbar_wait(&o_done[qt * NT + t - 1], 0);       // PV(t-1) retired: O is quiescent
           tc_fence_after();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t o[32];
-            tmem_ld32(o_addr + h * 32, o);
+          for (int h = 0; h < 4; ++h) {
+            uint32_t o[16];
+            tmem_ld16(o_addr + h * 16, o);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(o_addr + h * 32, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(o_addr + h * 16, o);
           }
         }
         if (need) m_used = mx;
       }
-      // ---- pass B: P = 2^(s * scale + rel_h + rel_w - m) for the 49 valid keys, 0 for the 15 padding columns ----
+      WTL(4);
+      // ---- P = 2^(x - m) for the 28 keys, 0 for the 4 padding columns; packed bf16 back over the slot ----
+      uint32_t pk[16];
 #pragma unroll
-      for (int a = 0; a < kNumRows[t]; ++a) hrow[a] -= m_used;
-#pragma unroll
-      for (int pc = 0; pc < 4; ++pc) {
-        uint32_t b[16];
-        tmem_ld16(tbase + pc * 16, b);
-        tmem_wait_ld();
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float p[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int c = pc * 16 + i + u;
-            if (c < W::TK) {
-              const int key = W::TK * t + c;
-              const int kh = key / W::GRID - kFirstRow[t], kw = key % W::GRID;
-              p[u] = ex2(fmaf(__uint_as_float(b[i + u]), cs, hrow[kh]) + w[kw]);
-            } else {
-              p[u] = 0.f;
-            }
-          }
-          l0 += p[0];
-          l1 += p[1];
-          pk[i >> 1] = pack_bf16(p[0], p[1]);
-        }
-        tmem_st8(tbase + pc * 8, pk);    // overwrites score columns [8 pc, 8 pc + 8): read by piece pc / 2 <= pc
+      for (int c = 0; c < 28; c += 2) {
+        const float p0 = ex2(x[c] - m_used), p1 = ex2(x[c + 1] - m_used);
+        l0 += p0;
+        l1 += p1;
+        pk[c >> 1] = pack_bf16(p0, p1);
       }
+      pk[14] = 0u;
+      pk[15] = 0u;
+      tmem_st16(s_addr, pk);
+      WTL(5);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[qt * 4 + t]);
+      if (lane == 0) mbar_arrive(&p_ready[qt * NT + t]);
+      WTL(6);
     }
 
     // ---- epilogue: O / l -> out, window_unpartition + crop (image_encoder.py:267-289) ----
-    mbar_wait(&o_done[qt * 4 + 3], 0);
+    mbar_wait(&o_done[qt * NT + NT - 1], 0);
     tc_fence_after();
+    WTL(7);
+#if ULLSAM_WIN_TIMELINE
+    if (blockIdx.x == 300 && lane == 0 && quad == 0)
+      printf("win qt %d: wait tables %lld | gather %lld | per tile: wait S %lld, ld+bias+max %lld, rescale %lld, exp %lld, st+arrive %lld | wait last PV %lld | total %lld (since kernel start %lld)\n",
+             qt, wtl[0], wtl[1], wtl[2] / NT, wtl[3] / NT, wtl[4] / NT, wtl[5] / NT, wtl[6] / NT, wtl[7], clock64() - wtl_begin, clock64() - wtl_begin);
+#endif
     const float inv_l = 1.0f / (l0 + l1);
     long out_row = -1;
     if (tq < W::T) {
@@ -347,20 +361,24 @@ const char* launch_attention_windowed_v2(const __nv_bfloat16* q, const __nv_bflo
                                          const __nv_bfloat16* relh, const __nv_bfloat16* relw, int G, int heads,
                                          __nv_bfloat16* out, cudaStream_t stream) {
   const uint64_t rows = static_cast<uint64_t>(G) * heads * W::T;
-  CUtensorMap tq, tk, tv, trh, trw;
+  CUtensorMap tq, tq1, tk, tv, trh, trw;
   const char* e;
   if ((e = make_tmap_2d_bf16(&tq, q, rows, 64, 128, 64))) return e;
-  if ((e = make_tmap_2d_bf16(&tk, k, rows, 64, 64, 64))) return e;
-  if ((e = make_tmap_2d_bf16(&tv, v, rows, 64, 64, 64))) return e;
+  if ((e = make_tmap_2d_bf16(&tq1, q, rows, 64, W::Q1_ROWS, 64))) return e;
+  if ((e = make_tmap_2d_bf16(&tk, k, rows, 64, W::TN, 64))) return e;
+  if ((e = make_tmap_2d_bf16(&tv, v, rows, 64, W::TN, 64))) return e;
   if ((e = make_tmap_2d_bf16(&trh, relh, W::NREL, 64, W::NREL, 64))) return e;
   if ((e = make_tmap_2d_bf16(&trw, relw, W::NREL, 64, W::NREL, 64))) return e;
   static bool configured = false;
   if (!configured) {
     cudaError_t ce = cudaFuncSetAttribute(windowed_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W::TOTAL);
     if (ce != cudaSuccess) return cudaGetErrorString(ce);
+    // two CTAs of ~100 KB need the largest shared-memory carve-out
+    ce = cudaFuncSetAttribute(windowed_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (ce != cudaSuccess) return cudaGetErrorString(ce);
     configured = true;
   }
-  windowed_attention_kernel<<<G * heads, W::THREADS, W::TOTAL, stream>>>(tq, tk, tv, trh, trw, heads, out);
+  windowed_attention_kernel<<<G * heads, W::THREADS, W::TOTAL, stream>>>(tq, tq1, tk, tv, trh, trw, heads, out);
   cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? nullptr : cudaGetErrorString(ce);
 }
