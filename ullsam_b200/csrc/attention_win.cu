@@ -56,7 +56,7 @@ struct W {
   static constexpr int OFF_TABH = OFF_V + 6 * TILE_BYTES;
   static constexpr int OFF_SCR = OFF_V + NT * TILE_BYTES;   // fp32 [14][256]: rel_h of every row (and the rel_w scatter before it)
   static constexpr int OFF_BAR = OFF_SCR + 14 * 256 * 4;
-  static constexpr int NBAR = 2 + 2 * NT + 3 * 2 * NT;
+  static constexpr int NBAR = 2 + 2 * NT + 3 * 2 * NT + 2;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 256;                // per query tile: S/P slots [0,32) [32,64), O (tables first) [64,128)
 };
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(W::THREADS, 2)
 windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ1,
                           const __grid_constant__ CUtensorMap tmK,
                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmRh,
-                          const __grid_constant__ CUtensorMap tmRw, int heads, __nv_bfloat16* __restrict__ out) {
+                          const __grid_constant__ CUtensorMap tmRw, int heads, int nitems, __nv_bfloat16* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + W::OFF_BAR);
@@ -84,11 +84,30 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   uint64_t* s_full = v_full + NT;      // [qt][NT]
   uint64_t* p_ready = s_full + 2 * NT; // [qt][NT]
   uint64_t* o_done = p_ready + 2 * NT; // [qt][NT]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2 * NT);
+  uint64_t* epi_done = o_done + 2 * NT; // [qt]: the query tile's softmax warps have drained O (the next item's tables may land)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gh = blockIdx.x;                       // window * heads + head
-  const int row_base = gh * W::T;
+  // Persistent CTA: items (window * heads + head) blockIdx.x, blockIdx.x + gridDim.x, ...  Every mbarrier completes exactly
+  // one phase per item, so the wait parity of item number `it` is simply it & 1 and nothing is ever re-initialised.
+  auto issue_loads = [&](int gh) {   // Q, the bias tables, all K tiles and V tiles 0..4 of one item (one elected lane)
+    const int row_base = gh * W::T;
+    mbar_arrive_expect_tx(q_full, 16384 + W::Q1_ROWS * 128 + 2 * 4096);
+    tma_load_2d(smem + W::OFF_Q, &tmQ, q_full, 0, row_base);
+    tma_load_2d(smem + W::OFF_Q + 16384, &tmQ1, q_full, 0, row_base + 128);
+    tma_load_2d(smem + W::OFF_TABW, &tmRw, q_full, 0, 0);
+    tma_load_2d(smem + W::OFF_TABH, &tmRh, q_full, 0, 0);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      mbar_arrive_expect_tx(&k_full[t], W::TILE_BYTES);
+      tma_load_2d(smem + W::OFF_K + t * W::TILE_BYTES, &tmK, &k_full[t], 0, row_base + t * W::TK);
+    }
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+      mbar_arrive_expect_tx(&v_full[t], W::TILE_BYTES);
+      tma_load_2d(smem + W::OFF_V + t * W::TILE_BYTES, &tmV, &v_full[t], 0, row_base + t * W::TK);
+    }
+  };
 
   if (warp == 8) {
     if (elect_one_sync()) {
@@ -96,23 +115,11 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       mbar_init(pro_done, 2);   // one commit per MMA warp
       for (int i = 0; i < NT; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); }
       for (int i = 0; i < 2 * NT; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_done[i], 1); }
+      mbar_init(&epi_done[0], 4);
+      mbar_init(&epi_done[1], 4);
       fence_barrier_init();
-      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-      mbar_arrive_expect_tx(q_full, 16384 + W::Q1_ROWS * 128 + 2 * 4096);
-      tma_load_2d(smem + W::OFF_Q, &tmQ, q_full, 0, row_base);
-      tma_load_2d(smem + W::OFF_Q + 16384, &tmQ1, q_full, 0, row_base + 128);
-      tma_load_2d(smem + W::OFF_TABW, &tmRw, q_full, 0, 0);
-      tma_load_2d(smem + W::OFF_TABH, &tmRh, q_full, 0, 0);
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        mbar_arrive_expect_tx(&k_full[t], W::TILE_BYTES);
-        tma_load_2d(smem + W::OFF_K + t * W::TILE_BYTES, &tmK, &k_full[t], 0, row_base + t * W::TK);
-      }
-#pragma unroll
-      for (int t = 0; t < 5; ++t) {
-        mbar_arrive_expect_tx(&v_full[t], W::TILE_BYTES);
-        tma_load_2d(smem + W::OFF_V + t * W::TILE_BYTES, &tmV, &v_full[t], 0, row_base + t * W::TK);
-      }
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmQ1); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+      issue_loads(blockIdx.x);
     }
     __syncwarp();
   }
@@ -135,58 +142,71 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     const uint32_t sq = smem_u32(smem + W::OFF_Q) + qt * 16384, sk = smem_u32(smem + W::OFF_K), sv = smem_u32(smem + W::OFF_V);
     const uint32_t tq0 = tmem_base + qt * 128;
     const uint64_t dq = make_smem_desc_sw128(sq, 16, 1024);
-    mbar_wait(q_full, 0);
-    tc_fence_after();
-    if (leader) {
-      const uint64_t drw = make_smem_desc_sw128(smem_u32(smem + W::OFF_TABW), 16, 1024);
-      const uint64_t drh = make_smem_desc_sw128(smem_u32(smem + W::OFF_TABH), 16, 1024);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_ss(tq0 + 64, dq + 2 * k, drw + 2 * k, idesc_rel, k != 0);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_ss(tq0 + 96, dq + 2 * k, drh + 2 * k, idesc_rel, k != 0);
-      umma_commit(pro_done);
-    }
-    __syncwarp();
-    if (warp == 8) {
-      // V tiles 5, 6 share their slots with the tables: load them once BOTH warps' bias MMAs have retired
-      mbar_wait(pro_done, 0);
-      if (leader) {
-#pragma unroll
-        for (int t = 5; t < NT; ++t) {
-          mbar_arrive_expect_tx(&v_full[t], W::TILE_BYTES);
-          tma_load_2d(smem + W::OFF_V + t * W::TILE_BYTES, &tmV, &v_full[t], 0, row_base + t * W::TK);
-        }
-      }
-      __syncwarp();
-    }
-    auto issue_qk = [&](int t) {   // S[t & 1] = Q K(t)^T
-      mbar_wait(&k_full[t], 0);
-      tc_fence_after();
-      const uint64_t dk = make_smem_desc_sw128(sk + t * W::TILE_BYTES, 16, 1024);
-      if (leader) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tq0 + (t & 1) * 32, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
-        umma_commit(&s_full[qt * NT + t]);
-      }
-      __syncwarp();
-    };
-    issue_qk(0);
-    issue_qk(1);
+    const uint64_t drw = make_smem_desc_sw128(smem_u32(smem + W::OFF_TABW), 16, 1024);
+    const uint64_t drh = make_smem_desc_sw128(smem_u32(smem + W::OFF_TABH), 16, 1024);
 #pragma unroll 1
-    for (int t = 0; t < NT; ++t) {
-      mbar_wait(&v_full[t], 0);
-      const uint64_t dv = make_smem_desc_sw128(sv + t * W::TILE_BYTES, 16, 1024);
-      mbar_wait(&p_ready[qt * NT + t], 0);   // P(t) is in its slot (and, for t = 0, the tables are consumed)
+    for (int it = 0, gh = blockIdx.x; gh < nitems; ++it, gh += gridDim.x) {
+      const uint32_t ph = it & 1;
+      mbar_wait(q_full, ph);
+      if (it > 0) mbar_wait(&epi_done[qt], ph ^ 1);   // the previous item's O has been read out: the tables may overwrite it
       tc_fence_after();
       if (leader) {
 #pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2)
-          umma_ts(tq0 + 64, tq0 + (t & 1) * 32 + s2 * 8, dv + s2 * 128, idesc_pv, (t | s2) != 0);
-        umma_commit(&o_done[qt * NT + t]);
+        for (int k = 0; k < 4; ++k) umma_ss(tq0 + 64, dq + 2 * k, drw + 2 * k, idesc_rel, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tq0 + 96, dq + 2 * k, drh + 2 * k, idesc_rel, k != 0);
+        umma_commit(pro_done);
       }
       __syncwarp();
-      // the slot of tile t is free once PV(t) has read P(t); tcgen05 ops of one thread execute in order
-      if (t + 2 < NT) issue_qk(t + 2);
+      if (warp == 8) {
+        // V tiles 5, 6 share their slots with the tables: load them once BOTH warps' bias MMAs have retired
+        mbar_wait(pro_done, ph);
+        if (leader) {
+#pragma unroll
+          for (int t = 5; t < NT; ++t) {
+            mbar_arrive_expect_tx(&v_full[t], W::TILE_BYTES);
+            tma_load_2d(smem + W::OFF_V + t * W::TILE_BYTES, &tmV, &v_full[t], 0, gh * W::T + t * W::TK);
+          }
+        }
+        __syncwarp();
+      }
+      auto issue_qk = [&](int t) {   // S[t & 1] = Q K(t)^T
+        mbar_wait(&k_full[t], ph);
+        tc_fence_after();
+        const uint64_t dk = make_smem_desc_sw128(sk + t * W::TILE_BYTES, 16, 1024);
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tq0 + (t & 1) * 32, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+          umma_commit(&s_full[qt * NT + t]);
+        }
+        __syncwarp();
+      };
+      issue_qk(0);
+      issue_qk(1);
+#pragma unroll 1
+      for (int t = 0; t < NT; ++t) {
+        mbar_wait(&v_full[t], ph);
+        const uint64_t dv = make_smem_desc_sw128(sv + t * W::TILE_BYTES, 16, 1024);
+        mbar_wait(&p_ready[qt * NT + t], ph);   // P(t) is in its slot (and, for t = 0, the tables are consumed)
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2)
+            umma_ts(tq0 + 64, tq0 + (t & 1) * 32 + s2 * 8, dv + s2 * 128, idesc_pv, (t | s2) != 0);
+          umma_commit(&o_done[qt * NT + t]);
+        }
+        __syncwarp();
+        // the slot of tile t is free once PV(t) has read P(t); tcgen05 ops of one thread execute in order
+        if (t + 2 < NT) issue_qk(t + 2);
+      }
+      if (warp == 8 && gh + static_cast<int>(gridDim.x) < nitems) {
+        // every MMA of this item has retired (both query tiles): shared memory is free, the next item's loads overlap the
+        // epilogue of this one
+        mbar_wait(&o_done[0 * NT + NT - 1], ph);
+        mbar_wait(&o_done[1 * NT + NT - 1], ph);
+        if (leader) issue_loads(gh + gridDim.x);
+        __syncwarp();
+      }
     }
   } else {
     // ================================ softmax warps: one thread per query row ========================================
@@ -203,8 +223,11 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     long long wtl_last = clock64();
     const long long wtl_begin = wtl_last;
 #endif
+#pragma unroll 1
+    for (int it = 0, gh = blockIdx.x; gh < nitems; ++it, gh += gridDim.x) {
+    const uint32_t ph = it & 1;
     // ---- bias rows: w[kw] = Tw[row][qw - kw + 13] (registers), h[kh] = Th[row][qh - kh + 13] (shared memory) ----
-    mbar_wait(pro_done, 0);
+    mbar_wait(pro_done, ph);
     tc_fence_after();
     WTL(0);
     float w[14];
@@ -250,7 +273,7 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       const float h0 = scr[(2 * t) * 256 + col], h1 = scr[(2 * t + 1) * 256 + col];   // key-grid rows 2t, 2t+1
-      mbar_wait(&s_full[qt * NT + t], 0);
+      mbar_wait(&s_full[qt * NT + t], ph);
       tc_fence_after();
       WTL(2);
       const uint32_t s_addr = tbase + (t & 1) * 32;
@@ -277,7 +300,7 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         l0 *= alpha;
         l1 *= alpha;
         if (t > 0) {
-          mbar_wait(&o_done[qt * NT + t - 1], 0);       // PV(t-1) retired: O is quiescent
+          mbar_wait(&o_done[qt * NT + t - 1], ph);      // PV(t-1) retired: O is quiescent
           tc_fence_after();
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
@@ -313,7 +336,7 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     }
 
     // ---- epilogue: O / l -> out, window_unpartition + crop (image_encoder.py:267-289) ----
-    mbar_wait(&o_done[qt * NT + NT - 1], 0);
+    mbar_wait(&o_done[qt * NT + NT - 1], ph);
     tc_fence_after();
     WTL(7);
 #if ULLSAM_WIN_TIMELINE
@@ -330,21 +353,29 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       if (y < 64 && x < 64) out_row = static_cast<long>(b) * 4096 + y * 64 + x;
     }
     const int head = gh % heads;
+    uint32_t o0[32], o1[32];
+    tmem_ld32(o_addr, o0);
+    tmem_ld32(o_addr + 32, o1);
+    tmem_wait_ld();
+    // O is in registers: the next item's bias tables may be written over it
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&epi_done[qt]);
+    if (out_row >= 0) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (out_row * heads + head) * 64);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint32_t o[32];
-      tmem_ld32(o_addr + h * 32, o);
-      tmem_wait_ld();
-      if (out_row >= 0) {
-        uint4* dst = reinterpret_cast<uint4*>(out + (out_row * heads + head) * 64 + h * 32);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          dst[u] = make_uint4(pack_bf16(__uint_as_float(o[8 * u]) * inv_l, __uint_as_float(o[8 * u + 1]) * inv_l),
-                              pack_bf16(__uint_as_float(o[8 * u + 2]) * inv_l, __uint_as_float(o[8 * u + 3]) * inv_l),
-                              pack_bf16(__uint_as_float(o[8 * u + 4]) * inv_l, __uint_as_float(o[8 * u + 5]) * inv_l),
-                              pack_bf16(__uint_as_float(o[8 * u + 6]) * inv_l, __uint_as_float(o[8 * u + 7]) * inv_l));
+      for (int u = 0; u < 4; ++u) {
+        dst[u] = make_uint4(pack_bf16(__uint_as_float(o0[8 * u]) * inv_l, __uint_as_float(o0[8 * u + 1]) * inv_l),
+                            pack_bf16(__uint_as_float(o0[8 * u + 2]) * inv_l, __uint_as_float(o0[8 * u + 3]) * inv_l),
+                            pack_bf16(__uint_as_float(o0[8 * u + 4]) * inv_l, __uint_as_float(o0[8 * u + 5]) * inv_l),
+                            pack_bf16(__uint_as_float(o0[8 * u + 6]) * inv_l, __uint_as_float(o0[8 * u + 7]) * inv_l));
+        dst[4 + u] = make_uint4(pack_bf16(__uint_as_float(o1[8 * u]) * inv_l, __uint_as_float(o1[8 * u + 1]) * inv_l),
+                                pack_bf16(__uint_as_float(o1[8 * u + 2]) * inv_l, __uint_as_float(o1[8 * u + 3]) * inv_l),
+                                pack_bf16(__uint_as_float(o1[8 * u + 4]) * inv_l, __uint_as_float(o1[8 * u + 5]) * inv_l),
+                                pack_bf16(__uint_as_float(o1[8 * u + 6]) * inv_l, __uint_as_float(o1[8 * u + 7]) * inv_l));
       }
     }
+    }  // item loop
   }
 
   tc_fence_before();
@@ -378,7 +409,12 @@ const char* launch_attention_windowed_v2(const __nv_bfloat16* q, const __nv_bflo
     if (ce != cudaSuccess) return cudaGetErrorString(ce);
     configured = true;
   }
-  windowed_attention_kernel<<<G * heads, W::THREADS, W::TOTAL, stream>>>(tq, tq1, tk, tv, trh, trw, heads, out);
+  const int nitems = G * heads;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = nitems < 2 * sms ? nitems : 2 * sms;   // two resident CTAs per SM, each walks items grid apart
+  windowed_attention_kernel<<<grid, W::THREADS, W::TOTAL, stream>>>(tq, tq1, tk, tv, trh, trw, heads, nitems, out);
   cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? nullptr : cudaGetErrorString(ce);
 }
