@@ -54,8 +54,9 @@ struct W {
   static constexpr int OFF_V = OFF_K + NT * TILE_BYTES;
   static constexpr int OFF_TABW = OFF_V + 5 * TILE_BYTES;   // the two 4 KB tables ride in V tiles 5 and 6 until the bias MMAs retire
   static constexpr int OFF_TABH = OFF_V + 6 * TILE_BYTES;
-  static constexpr int OFF_SCR = OFF_V + NT * TILE_BYTES;   // fp32 [14][256]: rel_h of every row (and the rel_w scatter before it)
-  static constexpr int OFF_BAR = OFF_SCR + 14 * 256 * 4;
+  static constexpr int OFF_SCR = OFF_V + NT * TILE_BYTES;   // fp32 [14][256]: rel_h of every row
+  static constexpr int OFF_SCRW = OFF_SCR + 14 * 256 * 4;   // fp32 [14][256]: rel_w of every row
+  static constexpr int OFF_BAR = OFF_SCRW + 14 * 256 * 4;
   static constexpr int NBAR = 2 + 2 * NT + 3 * 2 * NT + 2;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 256;                // per query tile: S/P slots [0,32) [32,64), O (tables first) [64,128)
@@ -215,7 +216,8 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     const int tq = qt * 128 + r;               // query index inside the window (>= 196: padding rows of tile 1)
     const int qh = tq / W::GRID, qw = tq % W::GRID;
     const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + qt * 128;
-    float* scr = reinterpret_cast<float*>(smem + W::OFF_SCR);   // [14][256]
+    float* scr = reinterpret_cast<float*>(smem + W::OFF_SCR);    // [14][256] rel_h
+    float* scrw = reinterpret_cast<float*>(smem + W::OFF_SCRW);  // [14][256] rel_w
     const int col = qt * 128 + r;
 
 #if ULLSAM_WIN_TIMELINE
@@ -230,30 +232,22 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     mbar_wait(pro_done, ph);
     tc_fence_after();
     WTL(0);
-    float w[14];
-    float wmax = -INFINITY;
     {
-      uint32_t v[32];
+      // (both bias rows stay in shared memory and are re-read tile by tile: with 96 registers per thread a register copy
+      //  of the 14 rel_w values pushed other state into local memory)
+      uint32_t v[32], v2[32];
       tmem_ld32(tbase + 64, v);
+      tmem_ld32(tbase + 96, v2);
       tmem_wait_ld();
 #pragma unroll
       for (int i = 0; i < 27; ++i) {
         const int kk = qw + 13 - i;
-        if (kk >= 0 && kk < 14) scr[kk * 256 + col] = __uint_as_float(v[i]) * kLog2e;
+        if (kk >= 0 && kk < 14) scrw[kk * 256 + col] = __uint_as_float(v[i]) * kLog2e;
       }
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < 14; ++k) {
-        w[k] = scr[k * 256 + col];
-        wmax = fmaxf(wmax, w[k]);
-      }
-      __syncwarp();
-      tmem_ld32(tbase + 96, v);
-      tmem_wait_ld();
 #pragma unroll
       for (int i = 0; i < 27; ++i) {
         const int kk = qh + 13 - i;
-        if (kk >= 0 && kk < 14) scr[kk * 256 + col] = __uint_as_float(v[i]) * kLog2e;
+        if (kk >= 0 && kk < 14) scr[kk * 256 + col] = __uint_as_float(v2[i]) * kLog2e;
       }
       // rows >= 196 (qh >= 14) have no valid window position: give them finite zeros
       if (qh >= 14) {
@@ -268,11 +262,13 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     const float cs = 0.125f * kLog2e;
     float m_used = -INFINITY, l0 = 0.f, l1 = 0.f;
     const uint32_t o_addr = tbase + 64;
-    (void)wmax;
 
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       const float h0 = scr[(2 * t) * 256 + col], h1 = scr[(2 * t + 1) * 256 + col];   // key-grid rows 2t, 2t+1
+      float w[14];
+#pragma unroll
+      for (int k = 0; k < 14; ++k) w[k] = scrw[k * 256 + col];
       mbar_wait(&s_full[qt * NT + t], ph);
       tc_fence_after();
       WTL(2);
