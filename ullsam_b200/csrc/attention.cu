@@ -136,7 +136,8 @@ template <int GRID>
 __global__ void __launch_bounds__(AttCfg<GRID>::THREADS, AttCfg<GRID>::GLOBAL ? 1 : 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmRh,
-                 const __grid_constant__ CUtensorMap tmRw, int heads, __nv_bfloat16* __restrict__ out) {
+                 const __grid_constant__ CUtensorMap tmRw, int heads, const float* __restrict__ kmax_norm,
+                 __nv_bfloat16* __restrict__ out) {
   using A = AttCfg<GRID>;
   constexpr int KS = A::KSTAGES, VS = A::VSTAGES, BN = A::BN, NT = A::NT, QT = A::QT, NSLOT = A::NSLOT, NITEMS = A::NITEMS;
   constexpr int NROWS = A::NROWS;
@@ -392,7 +393,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // ---- prologue: scatter this row's 64 rel_w and 64 rel_h values (log2 units), remember max(rel_w) ----
       mbar_wait(pro_mma_done, 0);
       tc_fence_after();
-      float wmax = -INFINITY;
+      float wmax = -INFINITY, hmax_all = -INFINITY;
 #pragma unroll
       for (int tbl = 0; tbl < 2; ++tbl) {
         const uint32_t col_t = (tbl ? 256 : 0) + qt * 128;
@@ -409,6 +410,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               const float val = __uint_as_float(v[i]) * kLog2e;
               if (tbl) {
                 relh_s[kk * NROWS + tidq] = __float2half_rn(val);
+                hmax_all = fmaxf(hmax_all, val);
               } else {
                 relw_s[((kk >> 2) * NROWS + tidq) * 4 + (kk & 3)] = val;
                 wmax = fmaxf(wmax, val);
@@ -433,6 +435,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       float m_used = -INFINITY;          // reference point of the exponentials (log2 units)
       float l0 = 0.f, l1 = 0.f;          // row sum (two accumulation chains)
       const uint32_t o_addr = lane_addr + A::COL_O + qt * 64;
+      // A-priori bound of EVERY biased score of the row (Cauchy-Schwarz): |q| * max_k |k| * scale + max rel_w + max rel_h,
+      // with max_k |k| of this (image, head) from a tiny pre-pass over K (kmax_norm, may be null).  Once the reference
+      // point chosen on the first tile is within 2^100 of that bound nothing can overflow any more (P is bf16 with an
+      // 8-bit exponent, O and the row sum are fp32), so the maximum pass and the rescale check are skipped for the
+      // remaining 31 tiles; otherwise (huge norms) the kernel keeps checking tile by tile as before.
+      float bound_rest = INFINITY;
+      if (kmax_norm != nullptr) {
+        const uint8_t* qrow = smem + A::OFF_Q + qt * A::QBYTES + r * 128;   // 128-byte swizzle: 16-byte chunk c at c ^ (r & 7)
+        float qq = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = *reinterpret_cast<const uint4*>(qrow + ((c ^ (r & 7)) << 4));
+          const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f2 = __bfloat1622float2(b2[e]);
+            qq = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, qq));
+          }
+        }
+        bound_rest = fmaf(sqrtf(qq) * __ldg(kmax_norm + gh), cs, wmax + hmax_all) + 0.0625f;   // (+ slack for the half-rounded rel_h)
+      }
+      bool skip_max = false;
 
 #if ULLSAM_ATT_TIMELINE
       long long tl[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -448,9 +472,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         TL_STAMP(0);
 
-        // ---- pass A: maximum of the raw scores of the row (all four tcgen05.ld in flight at once) ----
         constexpr int PIECE = ULLSAM_ATT_PIECE, NP = 128 / PIECE;
         uint32_t pb[2][PIECE];
+        const float rh0 = __half2float(relh_s[(2 * j) * NROWS + tidq]);
+        const float rh1 = __half2float(relh_s[(2 * j + 1) * NROWS + tidq]);
+        if (skip_max) {
+          tmem_ld_n(s_addr, pb[0]);   // first piece of pass B
+        } else {
+        // ---- pass A: maximum of the raw scores of the row (all four tcgen05.ld in flight at once) ----
         float mxs;
         {
           uint32_t a0[32], a1[32], a2[32], a3[32];
@@ -475,8 +504,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
           mxs = fmaxf(fmaxf(fmax3(m0, m1, m2), fmax3(m3, m4, m5)), fmaxf(m6, m7));
         }
-        const float rh0 = __half2float(relh_s[(2 * j) * NROWS + tidq]);
-        const float rh1 = __half2float(relh_s[(2 * j + 1) * NROWS + tidq]);
         const float mx = fmaf(mxs, cs, wmax + fmaxf(rh0, rh1));
 
         // ---- lazy move of the reference point (whole warp: tcgen05.ld/st are collective) ----
@@ -507,6 +534,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (need) m_used = mx;
         }
 
+          // (the row may stop looking at maxima: see bound_rest)
+          skip_max = __all_sync(0xffffffffu, bound_rest <= m_used + 100.0f);
+        }
         TL_STAMP(2);
         // ---- pass B: P = 2^(s*scale + rel_h + rel_w - m), PIECE keys at a time, double-buffered TMEM reads ----
         // (small pieces keep the register pressure low enough for ptxas to issue the next tcgen05.ld early)
@@ -814,9 +844,40 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
+// max_t |k[gh][t][:]| per (group, head): the pre-pass behind the global kernel's a-priori score bound.
+// k: bf16 [GH][T][64].  One CTA per (group, head); 128 bytes per row, 16-byte loads.
+__global__ void __launch_bounds__(256) k_norm_max_kernel(const __nv_bfloat16* __restrict__ k, int T, float* __restrict__ out) {
+  __shared__ float red[8];
+  const uint4* base = reinterpret_cast<const uint4*>(k + static_cast<size_t>(blockIdx.x) * T * 64);
+  float mx = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float qq = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = __ldg(base + static_cast<size_t>(t) * 8 + c);
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f2 = __bfloat1622float2(b2[e]);
+        qq = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, qq));
+      }
+    }
+    mx = fmaxf(mx, qq);
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    out[blockIdx.x] = sqrtf(m);
+  }
+}
+
 template <int GRID>
 const char* launch_t(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* relh,
-                     const __nv_bfloat16* relw, int G, int heads, __nv_bfloat16* out, cudaStream_t stream) {
+                     const __nv_bfloat16* relw, int G, int heads, const float* kmax, __nv_bfloat16* out, cudaStream_t stream) {
   using A = AttCfg<GRID>;
   const uint64_t rows = static_cast<uint64_t>(G) * heads * A::T;
   CUtensorMap tq, tk, tv, trh, trw;
@@ -834,7 +895,7 @@ const char* launch_t(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     configured = true;
   }
   dim3 grid((A::T + A::NROWS - 1) / A::NROWS, G * heads);
-  kern<<<grid, A::THREADS, A::TOTAL, stream>>>(tq, tk, tv, trh, trw, heads, out);
+  kern<<<grid, A::THREADS, A::TOTAL, stream>>>(tq, tk, tv, trh, trw, heads, kmax, out);
   cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? nullptr : cudaGetErrorString(ce);
 }
@@ -843,15 +904,25 @@ const char* launch_t(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
 
 const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
                              const __nv_bfloat16* rel_h, const __nv_bfloat16* rel_w, int G, int heads, int grid,
-                             __nv_bfloat16* out, cudaStream_t stream) {
+                             __nv_bfloat16* out, cudaStream_t stream, float* kmax_scratch) {
   if (G <= 0) return nullptr;
-  if (grid == 64) return launch_t<64>(q, k, v, rel_h, rel_w, G, heads, out, stream);
+  if (grid == 64) {
+    // pre-pass: max key norm per (image, head) for the a-priori score bound (see the kernel); scratch of G * heads floats
+    // from the caller, or stream-ordered here
+    float* kmax = kmax_scratch;
+    if (kmax == nullptr && cudaMallocAsync(&kmax, static_cast<size_t>(G) * heads * sizeof(float), stream) != cudaSuccess)
+      return "attention: cudaMallocAsync failed";
+    k_norm_max_kernel<<<G * heads, 256, 0, stream>>>(k, 4096, kmax);
+    const char* e = launch_t<64>(q, k, v, rel_h, rel_w, G, heads, kmax, out, stream);
+    if (kmax_scratch == nullptr) cudaFreeAsync(kmax, stream);
+    return e;
+  }
   if (grid == 14) {
     if (G % 25 != 0) return "attention: windowed mode needs 25 windows per image";
     // default: the four-query-tiles-per-SM design (attention_win.cu); ULLSAM_WIN_ATT=1 selects the first design
     static const int win_ver = getenv("ULLSAM_WIN_ATT") ? atoi(getenv("ULLSAM_WIN_ATT")) : 2;
     if (win_ver == 2) return launch_attention_windowed_v2(q, k, v, rel_h, rel_w, G, heads, out, stream);
-    return launch_t<14>(q, k, v, rel_h, rel_w, G, heads, out, stream);
+    return launch_t<14>(q, k, v, rel_h, rel_w, G, heads, nullptr, out, stream);
   }
   return "attention: grid must be 64 (global) or 14 (windowed)";
 }

@@ -12,7 +12,8 @@ namespace ullsam {
 // grid == 14: G == 25*B windows of the 5x5 partition of the zero-padded 70x70 grid, padded query
 // rows are dropped on the store (image_encoder.py:224-289, 325-361).
 const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
-                             const __nv_bfloat16* rel_h, const __nv_bfloat16* rel_w, int G, int heads, int grid, __nv_bfloat16* out, cudaStream_t stream);
+                             const __nv_bfloat16* rel_h, const __nv_bfloat16* rel_w, int G, int heads, int grid, __nv_bfloat16* out, cudaStream_t stream,
+                             float* kmax_scratch = nullptr /* grid 64: G * heads floats (else allocated stream-ordered) */);
 
 // second windowed design (attention_win.cu): one CTA per (window, head), both query tiles, 4 key tiles of 49
 const char* launch_attention_windowed_v2(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,

@@ -103,6 +103,7 @@ struct ullsam_handle {
   int enc_cap = 0;
   float* x = nullptr;
   bf16 *xn = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *ao = nullptr, *hid = nullptr;
+  float* kmax = nullptr;  // [kEncChunk * heads] max key norm per (image, head): scratch of the global attention
   bf16* xn_t = nullptr;  // LayerNorm outputs in token order (xn holds the window-partitioned ones: its pad rows stay zero)
   float* emb_f32 = nullptr;  // [cap,256,4096] when the caller wants bf16 output / host staging
   int dec_cap_r = 0, dec_cap_nt = 0;
@@ -417,7 +418,7 @@ int check_ready(ullsam_handle* h, int which) {
 
 int ensure_encoder_ws(ullsam_handle* h, int B) {
   if (B <= h->enc_cap) return ULLSAM_OK;
-  for (void* p : {(void*)h->x, (void*)h->xn, (void*)h->xn_t, (void*)h->q, (void*)h->k, (void*)h->v, (void*)h->ao, (void*)h->hid,
+  for (void* p : {(void*)h->x, (void*)h->xn, (void*)h->xn_t, (void*)h->kmax, (void*)h->q, (void*)h->k, (void*)h->v, (void*)h->ao, (void*)h->hid,
                   (void*)h->emb_f32})
     dfree(h, p);
   const size_t D = h->cfg.embed_dim, M = h->cfg.mlp_dim;
@@ -425,13 +426,14 @@ int ensure_encoder_ws(ullsam_handle* h, int B) {
   h->x = dalloc<float>(h, tok * D);
   h->xn = dalloc<bf16>(h, tokw * D);
   h->xn_t = dalloc<bf16>(h, tok * D);
+  h->kmax = dalloc<float>(h, static_cast<size_t>(B) * h->cfg.num_heads);
   h->q = dalloc<bf16>(h, tokw * D);
   h->k = dalloc<bf16>(h, tokw * D);
   h->v = dalloc<bf16>(h, tokw * D);
   h->ao = dalloc<bf16>(h, tok * D);
   h->hid = dalloc<bf16>(h, tok * (M > 768 ? M : 768));
   h->emb_f32 = dalloc<float>(h, tok * 256);
-  if (!h->x || !h->xn || !h->xn_t || !h->q || !h->k || !h->v || !h->ao || !h->hid || !h->emb_f32) {
+  if (!h->x || !h->xn || !h->xn_t || !h->kmax || !h->q || !h->k || !h->v || !h->ao || !h->hid || !h->emb_f32) {
     h->enc_cap = 0;
     return fail(h, ULLSAM_ERR_NOMEM, "cudaMalloc failed for the encoder workspace");
   }
@@ -539,8 +541,8 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
       mark(h, PC_GEMM_QKV, st);
     }
     // attention (+ rel-pos bias, + window_unpartition)
-    CKS(launch_attention(h->q, h->k, h->v, b.relh, b.relw, b.global ? Bc : Bc * 25, heads, b.global ? 64 : 14, h->ao, st));
-    mark(h, b.global ? PC_ATTN_GLOBAL : PC_ATTN_WIN, st);
+    CKS(launch_attention(h->q, h->k, h->v, b.relh, b.relw, b.global ? Bc : Bc * 25, heads, b.global ? 64 : 14, h->ao, st, h->kmax));
+    mark(h, b.global ? PC_ATTN_GLOBAL : PC_ATTN_WIN, st, b.global ? 2 : 1);  // (global: key-norm pre-pass + attention)
     {  // proj + residual (+ norm2)
       GemmParams p = gp(tok, D, D);
       p.bias = b.proj_b; p.out = h->x; p.residual = h->x;
