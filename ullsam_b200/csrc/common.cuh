@@ -129,6 +129,14 @@ ULLSAM_DEVICE void fence_proxy_async_smem() {
 // ------------------------------------------------------------------------------------------
 // TMA
 // ------------------------------------------------------------------------------------------
+// Asynchronous L2 prefetch of `bytes` (multiple of 16) contiguous global bytes at a 16-byte aligned address.
+ULLSAM_DEVICE void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
+}
+// Per-thread L2 prefetch of the cache line holding gptr.
+ULLSAM_DEVICE void l2_prefetch_line(const void* gptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(gptr)) : "memory");
+}
 ULLSAM_DEVICE void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
@@ -295,6 +303,13 @@ ULLSAM_DEVICE uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 }
 ULLSAM_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Same without the release: the arrive orders nothing but itself.  (The .release form compiles to MEMBAR.ALL.GPU, which
+// stalls the warp until every global store it has issued is acknowledged — ncu: 9 % of the projection GEMM's epilogue.)
+// For "this TMEM buffer has been read" signals: the tcgen05.ld data is already in registers (tcgen05.wait::ld) and no
+// generic-proxy memory is handed over.
+ULLSAM_DEVICE void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion is signalled on a barrier that may live in the peer CTA of the pair
 ULLSAM_DEVICE void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {

@@ -24,6 +24,18 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps (the EW = 16 variant runs 640 threads)
 constexpr int GEMM_EPI_WARP0 = 4;
+#ifndef ULLSAM_GEMM_RES_PREFETCH
+#define ULLSAM_GEMM_RES_PREFETCH 0  // L2 prefetch of the next tile's addend: 1 = bulk, 2 = per line (measured: proj -3 %, lin2 +3 %)
+#endif
+#ifndef ULLSAM_GEMM_RELAXED_ARRIVE
+#define ULLSAM_GEMM_RELAXED_ARRIVE 1
+#endif
+#ifndef ULLSAM_GEMM_WIDE_F32_TMEM_PIPE
+#define ULLSAM_GEMM_WIDE_F32_TMEM_PIPE 0
+#endif
+#ifndef ULLSAM_GEMM_WIDE_F32
+#define ULLSAM_GEMM_WIDE_F32 1  // fp32 epilogues: full 128-byte lines per row + addend loads one chunk ahead
+#endif
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile —
 // each CTA stages its own 128 rows of A and its own BN/2 rows of W, the leader issues one 256 x BN x 16 MMA that
@@ -246,10 +258,63 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int COLS_PER_WARP = BN / (EW / 4);
     constexpr int NCHUNK = COLS_PER_WARP / 32;
     float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};  // EPI_RES_LN: row sums / sums of squares
+    // Residual epilogues: every lane asks L2 for its row's slice of the addend of the tile AFTER the one being drained
+    // (one tile period, ~10 us, ahead), so the epilogue's addend loads are L2 hits instead of DRAM round trips.
+    auto prefetch_addend = [&](int t) {
+#if ULLSAM_GEMM_RES_PREFETCH
+      if constexpr (kRes) {
+        if (t < num_tiles) {
+          const int r = ((t / tiles_n) * CG + cta_rank) * GEMM_BM + row_in_tile;
+          if (r < p.M) {
+            const float* src = p.residual + static_cast<size_t>(r) * p.ldc + (t % tiles_n) * BN + half * COLS_PER_WARP;
+#if ULLSAM_GEMM_RES_PREFETCH == 1
+            l2_prefetch_bulk(src, COLS_PER_WARP * 4);
+#else
+#pragma unroll
+            for (int b = 0; b < COLS_PER_WARP * 4; b += 128) l2_prefetch_line(reinterpret_cast<const uint8_t*>(src) + b);
+#endif
+          }
+        }
+      }
+#endif
+    };
+    prefetch_addend(tile_at(0));
+    // fp32 epilogues (kWide): a 32-column chunk is one 128-byte line per row, staged 16 rows at a time, so each global
+    // instruction covers 4 whole lines (8 lanes x 16 bytes per row).  The addend (residual stream / pos_embed) of chunk
+    // c+1 — across the tile boundary, of the next tile's first chunk — is requested before chunk c is processed: its
+    // DRAM latency is hidden behind a chunk of work or the wait for the accumulator (ncu before: 50 % of the
+    // projection GEMM's epilogue samples were long-scoreboard stalls on these loads).
+    constexpr bool kAdd = kRes || EPI == EPI_PATCH;
+    constexpr bool kWide = ULLSAM_GEMM_WIDE_F32 && EW == 8 && (EPI == EPI_RES_F32 || EPI == EPI_PATCH || EPI == EPI_F32);
+    constexpr bool kAddPipe = kWide && kAdd;
+    static_assert(!kAddPipe || NCHUNK % 2 == 0, "addend double buffer: the buffer index must wrap at the tile boundary");
+    float4 addbuf[2][2][4];
+    auto load_addend = [&](float4 (&dst)[2][4], int m_blk_, int n0_) {
+      const int base_row = m_blk_ * GEMM_BM + quad * 32 + (lane >> 3);
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int grow = base_row + h * 16 + i * 4;
+          dst[h][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grow < p.M) {
+            if constexpr (kRes)
+              dst[h][i] = *reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(grow) * p.ldc + n0_ + (lane & 7) * 4);
+            else
+              dst[h][i] = __ldg(reinterpret_cast<const float4*>(
+                  p.pos + static_cast<size_t>(grow % p.pos_rows) * p.N + n0_ + (lane & 7) * 4));
+          }
+        }
+    };
+    if constexpr (kAddPipe) {
+      const int t0 = tile_at(0);
+      if (t0 < num_tiles) load_addend(addbuf[0], (t0 / tiles_n) * CG + cta_rank, (t0 % tiles_n) * BN + half * COLS_PER_WARP);
+    }
     for (int it = 0, tile = tile_at(0); tile < num_tiles; tile = tile_at(++it)) {
       const int m_blk = (tile / tiles_n) * CG + cta_rank, n_blk = tile % tiles_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      prefetch_addend(tile_at(it + 1));
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = m_blk * GEMM_BM + row_in_tile;
@@ -483,13 +548,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // The TMEM load of chunk c+1 is in flight while chunk c is processed (two register buffers, loop fully
         // unrolled).  The GELU variant keeps the rolled loop: its per-chunk body is ~600 instructions and four
         // copies of it fall out of the instruction cache (measured: 972 -> 850 TFLOP/s when unrolled).
-        constexpr bool kPipe = (EPI != EPI_GELU_BF16) && EW == 8;  // (16 epilogue warps: 96 registers, no room for two buffers)
+        // (16 epilogue warps: 96 registers, no room for two buffers; with the addend double buffer neither)
+        constexpr bool kPipe = (EPI != EPI_GELU_BF16) && EW == 8 && !(kAddPipe && !ULLSAM_GEMM_WIDE_F32_TMEM_PIPE);
         uint32_t vbuf[2][32];
         if constexpr (kPipe) {
           tmem_ld32(taddr0, vbuf[0]);
           tmem_wait_ld();
         }
-#pragma unroll(kPipe ? NCHUNK : 1)
+#pragma unroll((kPipe || kAddPipe) ? NCHUNK : 1)
         for (int c = 0; c < NCHUNK; ++c) {
           const int n0 = col0 + c * 32;
           uint32_t (&v)[32] = vbuf[kPipe ? (c & 1) : 0];
@@ -502,7 +568,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // The addend (residual stream / pos_embed) of the whole 32-column chunk is requested up front,
           // so 8 independent 16-byte loads per lane are in flight while the accumulator is transposed.
           float4 add[2][4];
-          if constexpr (kRes || EPI == EPI_PATCH) {
+          if constexpr (kAddPipe) {
+            if (c + 1 < NCHUNK) {
+              load_addend(addbuf[(c + 1) & 1], m_blk, n0 + 32);
+            } else {
+              const int tn = tile_at(it + 1);
+              if (tn < num_tiles)
+                load_addend(addbuf[(c + 1) & 1], (tn / tiles_n) * CG + cta_rank, (tn % tiles_n) * BN + half * COLS_PER_WARP);
+            }
+          } else if constexpr (kAdd) {
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -580,6 +654,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
             __syncwarp();
+          } else if constexpr (kWide) {
+            // fp32 outputs, full lines: rows [16 h, 16 h + 16) of the warp's 32, 128 bytes each at a 144-byte pitch
+            // (conflict-free both ways); read back as 8 lanes x 16 bytes per row, 4 rows per instruction
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if ((lane >> 4) == h) {
+                float4* srow = reinterpret_cast<float4*>(stage + (lane & 15) * 144);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) srow[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r_in = i * 4 + (lane >> 3);
+                const int grow = tile_row0 + h * 16 + r_in;
+                float4 val = *reinterpret_cast<const float4*>(stage + r_in * 144 + (lane & 7) * 16);
+                if (grow < p.M) {
+                  if constexpr (kAdd) {
+                    const float4 a = addbuf[c & 1][h][i];
+                    val.x += a.x; val.y += a.y; val.z += a.z; val.w += a.w;
+                  }
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(grow) * p.ldc + n0 + (lane & 7) * 4) = val;
+                }
+              }
+              __syncwarp();
+            }
           } else {
             // fp32 outputs: two 16-column halves, 64 bytes per row each, same 80-byte pitch
 #pragma unroll
@@ -618,7 +718,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
+        if constexpr (CG == 2) {
+#if ULLSAM_GEMM_RELAXED_ARRIVE
+          mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
+#else
+          mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+#endif
+        }
         else mbar_arrive(&tempty_bar[acc]);
       }
       if constexpr (EPI == EPI_RES_LN) {
