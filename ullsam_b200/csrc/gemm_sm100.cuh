@@ -27,6 +27,9 @@ constexpr int GEMM_EPI_WARP0 = 4;
 #ifndef ULLSAM_GEMM_RES_PREFETCH
 #define ULLSAM_GEMM_RES_PREFETCH 0  // L2 prefetch of the next tile's addend: 1 = bulk, 2 = per line (measured: proj -3 %, lin2 +3 %)
 #endif
+#ifndef ULLSAM_GEMM_BIAS_SMEM
+#define ULLSAM_GEMM_BIAS_SMEM 1
+#endif
 #ifndef ULLSAM_GEMM_RELAXED_ARRIVE
 #define ULLSAM_GEMM_RELAXED_ARRIVE 1
 #endif
@@ -53,7 +56,11 @@ struct GemmSmem {
   // warp-private transpose tiles of the generic epilogues: 32 rows x 80-byte pitch per epilogue warp
   static constexpr int kStageBytesPerWarp = 32 * 80;
   static constexpr int kStageOffset = (kScratchOffset + 4 * 128 * 4 + 15) / 16 * 16;
-  static constexpr int kTotal = kStageOffset + EW * kStageBytesPerWarp + 1024 /* alignment slack */;
+  // warp-private copy of the bias slice of the current tile (generic epilogues): up to 128 floats per epilogue warp
+  static constexpr int kBiasBytesPerWarp = 512;
+  static constexpr int kBiasOffset = kStageOffset + EW * kStageBytesPerWarp;
+  static constexpr int kTotal = kBiasOffset + EW * kBiasBytesPerWarp + 1024 /* alignment slack */;
+  static_assert(kTotal <= 232448, "more than 227 KB of shared memory");
 };
 
 
@@ -306,6 +313,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
     };
+    // Generic epilogues: the bias slice of the NEXT tile is fetched into a register while the current tile is drained
+    // and parked in shared memory when that tile starts; the per-chunk reads are broadcast LDS.  (Loading it with
+    // __ldg inside the chunk loop exposed one L2 round trip per chunk: ncu, 600 of 2400 samples per epilogue warp.)
+#if ULLSAM_GEMM_BIAS_SMEM
+    float* bias_s = reinterpret_cast<float*>(smem + L::kBiasOffset + (warp - GEMM_EPI_WARP0) * L::kBiasBytesPerWarp);
+    float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool bias_lane = p.bias != nullptr && lane * 4 < COLS_PER_WARP;
+    static_assert(COLS_PER_WARP * 4 <= L::kBiasBytesPerWarp, "bias slice does not fit its shared-memory slot");
+    if (bias_lane && tile_at(0) < num_tiles)
+      bias_next = __ldg(reinterpret_cast<const float4*>(p.bias + (tile_at(0) % tiles_n) * BN + half * COLS_PER_WARP + lane * 4));
+#endif
     if constexpr (kAddPipe) {
       const int t0 = tile_at(0);
       if (t0 < num_tiles) load_addend(addbuf[0], (t0 / tiles_n) * CG + cta_rank, (t0 % tiles_n) * BN + half * COLS_PER_WARP);
@@ -535,6 +553,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // (4 lanes cover 64 contiguous bytes of one row, 8 rows per instruction) instead of 32 scattered rows. ----
         uint8_t* stage = smem + L::kStageOffset + (warp - GEMM_EPI_WARP0) * L::kStageBytesPerWarp;
         const int tile_row0 = m_blk * GEMM_BM + quad * 32;
+#if ULLSAM_GEMM_BIAS_SMEM
+        if (p.bias != nullptr) {
+          __syncwarp();  // every lane is done with the previous tile's slice
+          if (bias_lane) {
+            *reinterpret_cast<float4*>(bias_s + lane * 4) = bias_next;
+            const int tn = tile_at(it + 1);
+            if (tn < num_tiles)
+              bias_next = __ldg(reinterpret_cast<const float4*>(p.bias + (tn % tiles_n) * BN + half * COLS_PER_WARP + lane * 4));
+          }
+          __syncwarp();
+        }
+#endif
         const int rr = lane >> 2, cc = lane & 3;  // transposed phase: row-in-group, 16-byte column slot
         size_t qkv_row_off[4] = {0, 0, 0, 0};     // EPI_QKV: (g * heads * T + t) * 64 of the 4 rows this lane stores
         if constexpr (EPI == EPI_QKV) {
@@ -598,7 +628,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
+#if ULLSAM_GEMM_BIAS_SMEM
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
+#else
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+#endif
               f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
             }
           }
