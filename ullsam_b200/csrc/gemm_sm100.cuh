@@ -27,6 +27,13 @@ constexpr int GEMM_EPI_WARP0 = 4;
 #ifndef ULLSAM_GEMM_RES_PREFETCH
 #define ULLSAM_GEMM_RES_PREFETCH 0  // L2 prefetch of the next tile's addend: 1 = bulk, 2 = per line (measured: proj -3 %, lin2 +3 %)
 #endif
+// bit (j & 3) set: element j of a chunk takes the 16th power of the GELU's erf by RCP + squarings instead of LG2/EX2
+#ifndef ULLSAM_GELU_RCP_MASK
+#define ULLSAM_GELU_RCP_MASK 0x1  // measured on lin1: 0x0 512 us, 0x1 503, 0x5 506, 0xF 519
+#endif
+#ifndef ULLSAM_GEMM_EARLY_RELEASE
+#define ULLSAM_GEMM_EARLY_RELEASE 1
+#endif
 #ifndef ULLSAM_GEMM_BIAS_SMEM
 #define ULLSAM_GEMM_BIAS_SMEM 1
 #endif
@@ -339,6 +346,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool row_ok = row < p.M;
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * COLS_PER_WARP;
       const int col0 = n_blk * BN + half * COLS_PER_WARP;
+      // Hands this accumulator buffer back to the MMA warp.  The generic epilogues call it as soon as their last
+      // tcgen05.ld has landed in registers (before the math and the stores of the last chunk): the buffer is held for
+      // a shorter time, which matters when the epilogue's latency is close to the main loop's (lin1's GELU).
+      constexpr bool kEarlyRelease = ULLSAM_GEMM_EARLY_RELEASE && !(EPI == EPI_LN_BF16 || EPI == EPI_LN_NCHW ||
+                                                                  EPI == EPI_LN_RES || EPI == EPI_UP1 || EPI == EPI_MASK);
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) {
+#if ULLSAM_GEMM_RELAXED_ARRIVE
+            mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
+#else
+            mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+#endif
+          } else {
+            mbar_arrive(&tempty_bar[acc]);
+          }
+        }
+      };
 
       if constexpr (EPI == EPI_LN_BF16 || EPI == EPI_LN_NCHW) {
         // ---- LayerNorm2d across the BN (== N) channels of this token; two warps share a row ----
@@ -584,6 +611,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if constexpr (kPipe) {
           tmem_ld32(taddr0, vbuf[0]);
           tmem_wait_ld();
+          if constexpr (kEarlyRelease && NCHUNK == 1) release_acc();
         }
 #pragma unroll((kPipe || kAddPipe) ? NCHUNK : 1)
         for (int c = 0; c < NCHUNK; ++c) {
@@ -594,6 +622,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             tmem_ld32(taddr0 + c * 32, v);
             tmem_wait_ld();
+            if constexpr (kEarlyRelease) {
+              if (c == NCHUNK - 1) release_acc();
+            }
           }
           // The addend (residual stream / pos_embed) of the whole 32-column chunk is requested up front,
           // so 8 independent 16-byte loads per lane are in flight while the accumulator is transposed.
@@ -638,7 +669,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if constexpr (EPI == EPI_GELU_BF16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = ((ULLSAM_GELU_RCP_MASK >> (j & 3)) & 1) ? gelu_erf_rcp(f[j]) : gelu_erf(f[j]);
           }
           if constexpr (EPI == EPI_BF16 || EPI == EPI_F32) {
             if (p.pos != nullptr) {
@@ -745,22 +776,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if constexpr (kPipe) {
             if (c + 1 < NCHUNK) tmem_wait_ld();  // chunk c+1 has landed (it was in flight during the work above)
+            if constexpr (kEarlyRelease) {
+              if (c + 2 == NCHUNK) release_acc();
+            }
           }
         }
       }
-      // release this accumulator buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 2) {
-#if ULLSAM_GEMM_RELAXED_ARRIVE
-          mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
-#else
-          mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
-#endif
-        }
-        else mbar_arrive(&tempty_bar[acc]);
-      }
+      if constexpr (!kEarlyRelease) release_acc();
       if constexpr (EPI == EPI_RES_LN) {
         // ---- the LayerNorm that follows the residual add, once the last N tile of this row block is stored ----
         if (n_blk == tiles_n - 1) {
