@@ -25,7 +25,10 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps (the EW = 16 variant runs 640 threads)
 constexpr int GEMM_EPI_WARP0 = 4;
 #ifndef ULLSAM_GEMM_RES_PREFETCH
-#define ULLSAM_GEMM_RES_PREFETCH 0  // L2 prefetch of the next tile's addend: 1 = bulk, 2 = per line (measured: proj -3 %, lin2 +3 %)
+// L2 prefetch of the next tile's addend, one tile period ahead: 1 = bulk, 2 = per line; only for K <= 1024 (with
+// K = 3072 it cost lin2 3 %).  On top of the register-level prefetch (one chunk ahead, shorter than a DRAM round
+// trip under load): proj 213.5 -> 206.1 us.
+#define ULLSAM_GEMM_RES_PREFETCH 2
 #endif
 // bit (j & 3) set: element j of a chunk takes the 16th power of the GELU's erf by RCP + squarings instead of LG2/EX2
 #ifndef ULLSAM_GELU_RCP_MASK
@@ -277,7 +280,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     auto prefetch_addend = [&](int t) {
 #if ULLSAM_GEMM_RES_PREFETCH
       if constexpr (kRes) {
-        if (t < num_tiles) {
+        if (t < num_tiles && p.K <= 1024) {  // (short main loops only: with K = 3072 it competes with the operand loads)
           const int r = ((t / tiles_n) * CG + cta_rank) * GEMM_BM + row_in_tile;
           if (r < p.M) {
             const float* src = p.residual + static_cast<size_t>(r) * p.ldc + (t % tiles_n) * BN + half * COLS_PER_WARP;
