@@ -129,10 +129,6 @@ ULLSAM_DEVICE void fence_proxy_async_smem() {
 // ------------------------------------------------------------------------------------------
 // TMA
 // ------------------------------------------------------------------------------------------
-// Asynchronous L2 prefetch of `bytes` (multiple of 16) contiguous global bytes at a 16-byte aligned address.
-ULLSAM_DEVICE void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
-}
 // Per-thread L2 prefetch of the cache line holding gptr.
 ULLSAM_DEVICE void l2_prefetch_line(const void* gptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(gptr)) : "memory");

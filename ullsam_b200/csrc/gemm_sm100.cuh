@@ -25,10 +25,10 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps (the EW = 16 variant runs 640 threads)
 constexpr int GEMM_EPI_WARP0 = 4;
 #ifndef ULLSAM_GEMM_RES_PREFETCH
-// L2 prefetch of the next tile's addend, one tile period ahead: 1 = bulk, 2 = per line; only for K <= 1024 (with
+// L2 prefetch of the next tile's addend, one tile period ahead (0 = off); only for K <= 1024 (with
 // K = 3072 it cost lin2 3 %).  On top of the register-level prefetch (one chunk ahead, shorter than a DRAM round
 // trip under load): proj 213.5 -> 206.1 us.
-#define ULLSAM_GEMM_RES_PREFETCH 2
+#define ULLSAM_GEMM_RES_PREFETCH 1
 #endif
 // bit (j & 3) set: element j of a chunk takes the 16th power of the GELU's erf by RCP + squarings instead of LG2/EX2
 #ifndef ULLSAM_GELU_RCP_MASK
@@ -42,9 +42,6 @@ constexpr int GEMM_EPI_WARP0 = 4;
 #endif
 #ifndef ULLSAM_GEMM_RELAXED_ARRIVE
 #define ULLSAM_GEMM_RELAXED_ARRIVE 1
-#endif
-#ifndef ULLSAM_GEMM_WIDE_F32_TMEM_PIPE
-#define ULLSAM_GEMM_WIDE_F32_TMEM_PIPE 0
 #endif
 #ifndef ULLSAM_GEMM_WIDE_F32
 #define ULLSAM_GEMM_WIDE_F32 1  // fp32 epilogues: full 128-byte lines per row + addend loads one chunk ahead
@@ -284,12 +281,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int r = ((t / tiles_n) * CG + cta_rank) * GEMM_BM + row_in_tile;
           if (r < p.M) {
             const float* src = p.residual + static_cast<size_t>(r) * p.ldc + (t % tiles_n) * BN + half * COLS_PER_WARP;
-#if ULLSAM_GEMM_RES_PREFETCH == 1
-            l2_prefetch_bulk(src, COLS_PER_WARP * 4);
-#else
+            // (per-thread prefetch.global.L2; the bulk form, UBLKPF.L2, takes uniform registers and is serialised
+            //  over the 32 lanes by ptxas)
 #pragma unroll
             for (int b = 0; b < COLS_PER_WARP * 4; b += 128) l2_prefetch_line(reinterpret_cast<const uint8_t*>(src) + b);
-#endif
           }
         }
       }
@@ -609,7 +604,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // unrolled).  The GELU variant keeps the rolled loop: its per-chunk body is ~600 instructions and four
         // copies of it fall out of the instruction cache (measured: 972 -> 850 TFLOP/s when unrolled).
         // (16 epilogue warps: 96 registers, no room for two buffers; with the addend double buffer neither)
-        constexpr bool kPipe = (EPI != EPI_GELU_BF16) && EW == 8 && !(kAddPipe && !ULLSAM_GEMM_WIDE_F32_TMEM_PIPE);
+        // (keeping both double buffers was measured slower: proj 222 -> 234 us)
+        constexpr bool kPipe = (EPI != EPI_GELU_BF16) && EW == 8 && !kAddPipe;
         uint32_t vbuf[2][32];
         if constexpr (kPipe) {
           tmem_ld32(taddr0, vbuf[0]);
