@@ -919,9 +919,11 @@ const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, con
   }
   if (grid == 14) {
     if (G % 25 != 0) return "attention: windowed mode needs 25 windows per image";
-    // default: the four-query-tiles-per-SM design (attention_win.cu); ULLSAM_WIN_ATT=1 selects the first design
+    // default: the four-query-tiles-per-SM design (attention_win.cu); ULLSAM_WIN_ATT=1 selects the first design,
+    // ULLSAM_WIN_ATT=3 the whole-window one-shot design (attention_win4.cu, experimental: not yet run on hardware)
     static const int win_ver = getenv("ULLSAM_WIN_ATT") ? atoi(getenv("ULLSAM_WIN_ATT")) : 2;
     if (win_ver == 2) return launch_attention_windowed_v2(q, k, v, rel_h, rel_w, G, heads, out, stream);
+    if (win_ver == 3) return launch_attention_windowed_v3(q, k, v, rel_h, rel_w, G, heads, out, stream);  // experimental
     return launch_t<14>(q, k, v, rel_h, rel_w, G, heads, nullptr, out, stream);
   }
   return "attention: grid must be 64 (global) or 14 (windowed)";

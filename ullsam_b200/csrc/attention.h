@@ -15,8 +15,14 @@ const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, con
                              const __nv_bfloat16* rel_h, const __nv_bfloat16* rel_w, int G, int heads, int grid, __nv_bfloat16* out, cudaStream_t stream,
                              float* kmax_scratch = nullptr /* grid 64: G * heads floats (else allocated stream-ordered) */);
 
-// second windowed design (attention_win.cu): one CTA per (window, head), both query tiles, 4 key tiles of 49
+// second windowed design (attention_win.cu): one CTA per (window, head), both query tiles, 7 key tiles of 28
 const char* launch_attention_windowed_v2(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                                         const __nv_bfloat16* rel_h, const __nv_bfloat16* rel_w, int G, int heads,
+                                         __nv_bfloat16* out, cudaStream_t stream);
+
+// third windowed design (attention_win4.cu): whole window in one shot per query tile, one CTA per SM.
+// EXPERIMENTAL: selected by ULLSAM_WIN_ATT=3 only; not yet validated on hardware.
+const char* launch_attention_windowed_v3(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
                                          const __nv_bfloat16* rel_h, const __nv_bfloat16* rel_w, int G, int heads,
                                          __nv_bfloat16* out, cudaStream_t stream);
 
