@@ -83,6 +83,12 @@ void ullsam_destroy(ullsam_handle* h);
  * (bf16 GEMM operands, fp32 vectors) before the call returns — the caller keeps ownership. */
 int ullsam_set_weight(ullsam_handle* h, const char* state_dict_key, const void* data, int dtype,
                       const int64_t* shape, int ndim);
+/* Same, stream-ordered and without any host synchronisation: `data` must be a DEVICE pointer (or pinned host memory)
+ * that stays valid until the work queued on `stream` so far has run — e.g. a torch tensor allocated on that stream.
+ * The copy and the re-pack kernels are queued on `stream`; the next forward call on a different stream waits for them
+ * on the device.  Loading a 316-tensor state_dict this way costs 316 enqueues instead of 316 device synchronisations. */
+int ullsam_set_weight_async(ullsam_handle* h, const char* state_dict_key, const void* data, int dtype,
+                            const int64_t* shape, int ndim, void* stream);
 /* Number of state_dict tensors still missing (0 when both modules are fully loaded). */
 int ullsam_missing_weights(const ullsam_handle* h, int which /*0 encoder, 1 decoder*/);
 

@@ -102,12 +102,22 @@ def test_module_shims_refuse_cpu_and_autograd():
 
     dec = MaskDecoder(transformer_dim=256, transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048,
                                                                          num_heads=8))
-    with pytest.raises(_lib.UllsamError, match="no CPU fallback"):
+    with torch.no_grad(), pytest.raises(_lib.UllsamError, match="no CPU fallback"):
         dec(torch.zeros(1, 256, 64, 64), torch.zeros(1, 256, 64, 64), torch.zeros(1, 2, 256),
             torch.zeros(1, 256, 64, 64), False)
+    # grad mode on + trainable parameters (the reference's training loop, train_joint_v2.py:1015-1063: the inputs never
+    # require grad, the parameters do): a backward would be expected, so the forward-only shim must refuse
+    with pytest.raises(_lib.UllsamError, match="forward pass only"):
+        dec(torch.zeros(1, 256, 64, 64), torch.zeros(1, 256, 64, 64), torch.zeros(1, 2, 256),
+            torch.zeros(1, 256, 64, 64), False)
+    dec.requires_grad_(False)
     x = torch.zeros(1, 256, 64, 64, requires_grad=True)
     with pytest.raises(_lib.UllsamError, match="forward pass only"):
         dec(x, torch.zeros(1, 256, 64, 64), torch.zeros(1, 2, 256), torch.zeros(1, 256, 64, 64), False)
+    # frozen module + inputs without grad: passes the autograd check even with grad mode on (and then fails on the device)
+    with pytest.raises(_lib.UllsamError, match="no CPU fallback"):
+        dec(torch.zeros(1, 256, 64, 64), torch.zeros(1, 256, 64, 64), torch.zeros(1, 2, 256),
+            torch.zeros(1, 256, 64, 64), False)
     with pytest.raises(_lib.UllsamError, match="specialised"):
         TwoWayTransformer(depth=2, embedding_dim=128, mlp_dim=2048, num_heads=8)
 

@@ -33,6 +33,8 @@ class _FakeEngine:
         return images.mean(dim=(1, 2, 3), keepdim=True).expand(-1, 4, 2, 2).contiguous()
 
     def decoder_forward(self, emb, pe, sparse, dense, multimask, prompts_per_image=1):
+        if emb.shape[0] == 0:   # like the C ABI: "decoder: n_img, P must be positive"
+            raise RuntimeError("decoder: n_img, P must be positive")
         m = emb[:, :1] + sparse.sum(dim=(1, 2)).reshape(-1, 1, 1, 1) + dense.sum() + pe.sum()
         return m.contiguous(), m.mean(dim=(2, 3))
 
@@ -57,7 +59,7 @@ def _worker(rank, world, port, n, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [8, 7])
+@pytest.mark.parametrize("n", [8, 7, 1])   # 1: fewer images than ranks, rank 1 holds an empty shard
 def test_two_rank_gloo_shard_and_gather(n):
     from ullsam_b200.parallel import segment_sharded
 

@@ -68,6 +68,27 @@ def test_llm_conditioned_point_prompts_vs_reference_golden(ctx):
     _close(dense_bf, O.dense_from_llm(ctx["sd"], llm.bfloat16().float()), 2e-5, "bf16 LLM map vs oracle")
 
 
+def test_bf16_module_llm_dense_uses_its_own_scale_and_bias(ctx):
+    """The reference runs the prompt encoder in bfloat16 (app.py:343-345, train_joint_v2.py:1675-1676).  The fp32 copies
+    of llm_scale_factor / llm_bias made for the kernel must both be alive when it runs: a freed temporary is handed to
+    the next one by the caching allocator and the kernel would read scale == bias (round-1 advisor finding).  A non-zero
+    bias that differs from the scale makes that aliasing visible."""
+    import copy
+
+    pe = copy.deepcopy(ctx["pe"]).bfloat16()
+    with torch.no_grad():
+        pe.llm_scale_factor.fill_(0.25)
+        pe.llm_bias.fill_(-0.5)
+    llm = synth.make_llm_map(2, seed=ctx["seed"] + 9, C=256, g=64)
+    coords, labels = synth.make_points(2, 1024, seed=ctx["seed"] + 2)
+    with torch.no_grad():
+        _, dense = pe(points=(coords.cuda(), labels.cuda()), boxes=None, masks=None, llm_hidden_states=llm.cuda().bfloat16())
+    x = llm.bfloat16().float()
+    ref = torch.nn.functional.layer_norm(x.flatten(2).transpose(1, 2), (256,), eps=1e-5).transpose(1, 2).reshape(x.shape)
+    ref = ref * 0.25 - 0.5                      # prompt_encoder.py:131-151
+    _close(dense, ref, 2e-5, "bf16 module: LLM-conditioned dense prompt")
+
+
 @pytest.mark.parametrize("with_box", [False, True])
 def test_mixed_labels_and_padding_rule_vs_oracle(ctx, with_box):
     gen = torch.Generator().manual_seed(3)

@@ -91,6 +91,8 @@ PROTOTYPES = {
     "ullsam_create": (C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(C.c_void_p)]),
     "ullsam_destroy": (None, [C.c_void_p]),
     "ullsam_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int]),
+    "ullsam_set_weight_async": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int,
+                                          C.c_void_p]),
     "ullsam_missing_weights": (C.c_int, [C.c_void_p, C.c_int]),
     "ullsam_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "ullsam_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

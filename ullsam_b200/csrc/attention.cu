@@ -28,6 +28,7 @@
 // (global: rel_w fp32 in [kw/4][row][4] order for conflict-free 16-byte reads, rel_h as halves) or keeps them
 // in registers (windowed).
 #include "attention.h"
+#include "host_util.h"
 
 #include <stdlib.h>
 // 1: global attention with ONE thread per query row (8 softmax warps, row-max bound instead of an exchange);
@@ -887,13 +888,9 @@ const char* launch_t(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
   if ((e = make_tmap_2d_bf16(&tv, v, rows, 64, A::BN, 64))) return e;
   if ((e = make_tmap_2d_bf16(&trh, relh, A::NREL, 64, A::NREL, 64))) return e;
   if ((e = make_tmap_2d_bf16(&trw, relw, A::NREL, 64, A::NREL, 64))) return e;
-  static bool configured = false;
+  static PerDeviceOnce configured;
   auto kern = attention_kernel<GRID>;
-  if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A::TOTAL);
-    if (ce != cudaSuccess) return cudaGetErrorString(ce);
-    configured = true;
-  }
+  if ((e = set_max_smem_once(configured, kern, A::TOTAL))) return e;
   dim3 grid((A::T + A::NROWS - 1) / A::NROWS, G * heads);
   kern<<<grid, A::THREADS, A::TOTAL, stream>>>(tq, tk, tv, trh, trw, heads, kmax, out);
   cudaError_t ce = cudaGetLastError();
@@ -919,11 +916,11 @@ const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, con
   }
   if (grid == 14) {
     if (G % 25 != 0) return "attention: windowed mode needs 25 windows per image";
-    // default: the four-query-tiles-per-SM design (attention_win.cu); ULLSAM_WIN_ATT=1 selects the first design,
-    // ULLSAM_WIN_ATT=3 the whole-window one-shot design (attention_win4.cu, experimental: not yet run on hardware)
+    // default: the four-query-tiles-per-SM design (attention_win.cu); ULLSAM_WIN_ATT=1 selects the first design.
+    // (A third, whole-window one-shot design was measured on B200 in round 2: parity-green but 0.475 ms against
+    //  0.414 ms per launch for this one, so it was removed — profiles/README.md.)
     static const int win_ver = getenv("ULLSAM_WIN_ATT") ? atoi(getenv("ULLSAM_WIN_ATT")) : 2;
     if (win_ver == 2) return launch_attention_windowed_v2(q, k, v, rel_h, rel_w, G, heads, out, stream);
-    if (win_ver == 3) return launch_attention_windowed_v3(q, k, v, rel_h, rel_w, G, heads, out, stream);  // experimental
     return launch_t<14>(q, k, v, rel_h, rel_w, G, heads, nullptr, out, stream);
   }
   return "attention: grid must be 64 (global) or 14 (windowed)";

@@ -20,10 +20,4 @@ const char* launch_attention_windowed_v2(const __nv_bfloat16* q, const __nv_bflo
                                          const __nv_bfloat16* rel_h, const __nv_bfloat16* rel_w, int G, int heads,
                                          __nv_bfloat16* out, cudaStream_t stream);
 
-// third windowed design (attention_win4.cu): whole window in one shot per query tile, one CTA per SM.
-// EXPERIMENTAL: selected by ULLSAM_WIN_ATT=3 only; not yet validated on hardware.
-const char* launch_attention_windowed_v3(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
-                                         const __nv_bfloat16* rel_h, const __nv_bfloat16* rel_w, int G, int heads,
-                                         __nv_bfloat16* out, cudaStream_t stream);
-
 }  // namespace ullsam

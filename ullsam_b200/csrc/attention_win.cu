@@ -20,6 +20,7 @@
 // (so the two tiles' QK -> softmax -> PV chains do not wait for each other; one of them also issues the TMA loads);
 // 2 CTAs / SM.
 #include "attention.h"
+#include "host_util.h"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -396,15 +397,9 @@ const char* launch_attention_windowed_v2(const __nv_bfloat16* q, const __nv_bflo
   if ((e = make_tmap_2d_bf16(&tv, v, rows, 64, W::TN, 64))) return e;
   if ((e = make_tmap_2d_bf16(&trh, relh, W::NREL, 64, W::NREL, 64))) return e;
   if ((e = make_tmap_2d_bf16(&trw, relw, W::NREL, 64, W::NREL, 64))) return e;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(windowed_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W::TOTAL);
-    if (ce != cudaSuccess) return cudaGetErrorString(ce);
-    // two CTAs of ~100 KB need the largest shared-memory carve-out
-    ce = cudaFuncSetAttribute(windowed_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (ce != cudaSuccess) return cudaGetErrorString(ce);
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  // two CTAs of ~100 KB need the largest shared-memory carve-out
+  if ((e = set_max_smem_once(configured, windowed_attention_kernel, W::TOTAL, 100))) return e;
   const int nitems = G * heads;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);

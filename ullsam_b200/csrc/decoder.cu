@@ -7,6 +7,7 @@
 //
 // Reference: modeling/transformer.py:62-242, modeling/mask_decoder.py:112-176.
 #include "decoder.h"
+#include "host_util.h"
 
 #include "common.cuh"
 
@@ -401,12 +402,8 @@ const char* launch_t2i_attention(const float* q, const __nv_bfloat16* kv, int ld
 const char* launch_i2t_attention(const __nv_bfloat16* proj, int ldp, int q_col, const float* k, const float* v, int R,
                                  int Nt, __nv_bfloat16* out, cudaStream_t stream) {
   if (Nt > 32) {
-    static bool configured = false;
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(i2t_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 320 * 4);
-      if (e != cudaSuccess) return cudaGetErrorString(e);
-      configured = true;
-    }
+    static PerDeviceOnce configured;
+    if (const char* ce = set_max_smem_once(configured, i2t_attention_kernel, 64 * 320 * 4)) return ce;
   }
   i2t_attention_kernel<<<dim3(128, R), 256, Nt * 320 * sizeof(float), stream>>>(proj, ldp, q_col, k, v, Nt, out);
   return last_err();

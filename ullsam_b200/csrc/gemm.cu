@@ -1,5 +1,6 @@
 // ullsam_b200 — host side of the tcgen05 GEMM: TMA tensor-map construction and launch.
 #include "gemm.h"
+#include "host_util.h"
 
 #include <cudaTypedefs.h>
 
@@ -59,13 +60,9 @@ template <int EPI, int EW>
 static const char* launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                                cudaStream_t stream) {
   using L = GemmSmem<256, 2, EW>;
-  static bool configured = false;
+  static PerDeviceOnce configured;
   auto kern = gemm_kernel<256, EPI, 2, EW>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-    if (e != cudaSuccess) return cudaGetErrorString(e);
-    configured = true;
-  }
+  if (const char* ce = set_max_smem_once(configured, kern, L::kTotal)) return ce;
   const int tiles = ((p.M + 255) / 256) * (p.N / 256);
   const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
   cudaLaunchConfig_t cfg{};
@@ -88,13 +85,9 @@ template <int BN, int EPI>
 static const char* launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                             cudaStream_t stream) {
   using L = GemmSmem<BN>;
-  static bool configured = false;
+  static PerDeviceOnce configured;
   auto kern = gemm_kernel<BN, EPI>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-    if (e != cudaSuccess) return cudaGetErrorString(e);
-    configured = true;
-  }
+  if (const char* ce = set_max_smem_once(configured, kern, L::kTotal)) return ce;
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * (p.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   kern<<<grid, GEMM_THREADS, L::kTotal, stream>>>(ta, tb, p);

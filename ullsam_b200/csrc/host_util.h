@@ -1,0 +1,63 @@
+// ullsam_b200 — host-side helpers shared by the kernel launchers.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+
+namespace ullsam {
+
+// "Has this kernel been configured on the CURRENT device yet?"  cudaFuncSetAttribute is per device (context), so a
+// process that drives several GPUs has to set MaxDynamicSharedMemorySize on each of them; one flag bit per device,
+// updated atomically (launchers may be called from several host threads, one per handle).
+struct PerDeviceOnce {
+  std::atomic<uint64_t> done{0};
+  // returns true exactly when the caller still has to configure the current device (and then must call mark())
+  bool needed(int* dev_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *dev_out = dev;
+    return dev < 0 || dev >= 64 || !(done.load(std::memory_order_acquire) & (1ull << dev));
+  }
+  void mark(int dev) {
+    if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+  }
+};
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per device; returns an error string or nullptr.
+template <typename Kern>
+inline const char* set_max_smem_once(PerDeviceOnce& once, Kern kern, int bytes, int carveout_percent = -1) {
+  int dev = 0;
+  if (!once.needed(&dev)) return nullptr;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return cudaGetErrorString(e);
+  if (carveout_percent >= 0) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+  }
+  once.mark(dev);
+  return nullptr;
+}
+
+// RAII: make `device` current for the duration of an ABI call and restore the caller's device afterwards
+// (PyTorch tracks the current device per thread; an ABI call must not change it behind its back).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t status = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    status = cudaGetDevice(&prev);
+    if (status == cudaSuccess && prev != device) {
+      status = cudaSetDevice(device);
+      switched = (status == cudaSuccess);
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+}  // namespace ullsam

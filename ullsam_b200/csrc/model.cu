@@ -16,6 +16,7 @@
 #include "decoder.h"
 #include "elementwise.h"
 #include "gemm.h"
+#include "host_util.h"
 
 using namespace ullsam;
 using bf16 = __nv_bfloat16;
@@ -76,6 +77,11 @@ struct ullsam_handle {
   bool alloc_failed = false;
   std::vector<void*> allocs;
   std::unordered_map<std::string, Slot> slots;
+  // weight upload: copies and re-pack kernels run on the legacy default stream without a host sync per tensor; the first
+  // forward call after an upload makes its stream wait for `weights_ev`
+  bool weights_dirty = false;
+  cudaStream_t weights_stream = 0;
+  cudaEvent_t weights_ev = nullptr;
   float* staging = nullptr;
   size_t staging_bytes = 0;
   void* staging_raw = nullptr;
@@ -167,6 +173,24 @@ void mark(ullsam_handle* h, int cat, cudaStream_t st, int nkernels = 1) {
     if (_c != cudaSuccess) return fail(h, ULLSAM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_c)); \
   } while (0)
 
+// make the handle's device current for the rest of the scope, restoring the caller's device on exit
+#define DEVICE_GUARD(h)                                                                        \
+  DeviceGuard _dev_guard((h)->device);                                                         \
+  if (_dev_guard.status != cudaSuccess)                                                        \
+  return fail(h, ULLSAM_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(_dev_guard.status))
+
+// order the caller's stream after any weight upload still in flight on the legacy default stream
+int weights_fence(ullsam_handle* h, cudaStream_t st) {
+  if (!h->weights_dirty) return ULLSAM_OK;
+  if (!h->weights_ev) CKC(cudaEventCreateWithFlags(&h->weights_ev, cudaEventDisableTiming));
+  if (st != h->weights_stream) {
+    CKC(cudaEventRecord(h->weights_ev, h->weights_stream));
+    CKC(cudaStreamWaitEvent(st, h->weights_ev, 0));
+  }
+  h->weights_dirty = false;
+  return ULLSAM_OK;
+}
+
 template <typename T>
 T* dalloc(ullsam_handle* h, size_t count, bool zero = false) {
   void* p = nullptr;
@@ -186,12 +210,15 @@ void dfree(ullsam_handle* h, void* p) {
   cudaFree(p);
 }
 
+// stream the re-pack kernels of the weight upload in progress run on (set by set_weight_impl around Slot::pack)
+thread_local cudaStream_t g_pack_stream = 0;
+
 template <typename TOut>
 const char* pack(const float* src, TOut* dst, int d0, int d1, int d2, int d3, long s0, long s1, long s2, long s3) {
   const size_t total = static_cast<size_t>(d0) * d1 * d2 * d3;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_kernel<TOut><<<static_cast<int>(blocks), 256>>>(src, dst, total, d1, d2, d3, s0, s1, s2, s3);
+  pack_kernel<TOut><<<static_cast<int>(blocks), 256, 0, g_pack_stream>>>(src, dst, total, d1, d2, d3, s0, s1, s2, s3);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -778,7 +805,8 @@ int ullsam_create(const ullsam_config* cfg, int device, ullsam_handle** out) {
   if (cfg->transformer_dim != 256 || cfg->dec_heads != 8 || cfg->num_mask_tokens != 4 || cfg->dec_mlp_dim % 4 != 0 ||
       cfg->dec_mlp_dim > 2048 || cfg->iou_head_hidden != 256 || cfg->iou_head_depth < 2 || cfg->dec_depth < 1)
     return fail(nullptr, ULLSAM_ERR_INVALID, "create: decoder must be SAM's (dim 256, 8 heads, 4 mask tokens, mlp <= 2048)");
-  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, ULLSAM_ERR_CUDA, "create: cudaSetDevice failed");
+  DeviceGuard guard(device);
+  if (guard.status != cudaSuccess) return fail(nullptr, ULLSAM_ERR_CUDA, "create: cudaSetDevice failed");
   ullsam_handle* h = new ullsam_handle();
   h->cfg = *cfg;
   h->device = device;
@@ -795,16 +823,22 @@ int ullsam_create(const ullsam_config* cfg, int device, ullsam_handle** out) {
 
 void ullsam_destroy(ullsam_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  if (h->weights_ev) cudaEventDestroy(h->weights_ev);
   if (h->staging) cudaFree(h->staging);
   if (h->staging_raw) cudaFree(h->staging_raw);
   delete h;
 }
 
-int ullsam_set_weight(ullsam_handle* h, const char* key, const void* data, int dtype, const int64_t* shape, int ndim) {
+}  // extern "C"
+
+namespace {
+// copies + re-packs one state_dict tensor, stream-ordered on `st`, no host synchronisation
+int set_weight_impl(ullsam_handle* h, const char* key, const void* data, int dtype, const int64_t* shape, int ndim,
+                    cudaStream_t st) {
   if (!h || !key || !data || (!shape && ndim > 0)) return fail(h, ULLSAM_ERR_INVALID, "set_weight: null argument");
   auto it = h->slots.find(key);
   if (it == h->slots.end()) return fail(h, ULLSAM_ERR_INVALID, std::string("set_weight: unknown state_dict key ") + key);
@@ -816,7 +850,7 @@ int ullsam_set_weight(ullsam_handle* h, const char* key, const void* data, int d
     n *= static_cast<size_t>(shape[i]);
   }
   if (!same) return fail(h, ULLSAM_ERR_INVALID, std::string("set_weight: shape mismatch for ") + key);
-  CKC(cudaSetDevice(h->device));
+  DEVICE_GUARD(h);
   if (h->staging_bytes < n * 4) {
     if (h->staging) cudaFree(h->staging);
     h->staging = nullptr;
@@ -825,7 +859,7 @@ int ullsam_set_weight(ullsam_handle* h, const char* key, const void* data, int d
     h->staging_bytes = n * 4;
   }
   if (dtype == ULLSAM_F32) {
-    CKC(cudaMemcpy(h->staging, data, n * 4, cudaMemcpyDefault));
+    CKC(cudaMemcpyAsync(h->staging, data, n * 4, cudaMemcpyDefault, st));
   } else if (dtype == ULLSAM_BF16 || dtype == ULLSAM_F16) {
     if (h->staging_raw_bytes < n * 2) {
       if (h->staging_raw) cudaFree(h->staging_raw);
@@ -834,15 +868,49 @@ int ullsam_set_weight(ullsam_handle* h, const char* key, const void* data, int d
       CKC(cudaMalloc(&h->staging_raw, n * 2));
       h->staging_raw_bytes = n * 2;
     }
-    CKC(cudaMemcpy(h->staging_raw, data, n * 2, cudaMemcpyDefault));
-    CKS(launch_cast_to_f32(h->staging_raw, dtype, n, h->staging, 0));
+    CKC(cudaMemcpyAsync(h->staging_raw, data, n * 2, cudaMemcpyDefault, st));
+    CKS(launch_cast_to_f32(h->staging_raw, dtype, n, h->staging, st));
   } else {
     return fail(h, ULLSAM_ERR_INVALID, "set_weight: dtype must be f32, bf16 or f16");
   }
-  CKS(s.pack(h->staging));
-  CKC(cudaDeviceSynchronize());
+  // Everything above is ordered on `st` (the staging buffers are reused tensor after tensor in stream order; cudaFree
+  // of an outgrown buffer synchronises by itself), so there is no host sync per tensor: the next forward call fences
+  // its stream against this one once (weights_fence).
+  g_pack_stream = st;
+  const char* pe = s.pack(h->staging);
+  g_pack_stream = 0;
+  if (pe) return fail(h, ULLSAM_ERR_CUDA, pe);
+  h->weights_dirty = true;
   s.loaded = true;
   return ULLSAM_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ullsam_set_weight(ullsam_handle* h, const char* key, const void* data, int dtype, const int64_t* shape, int ndim) {
+  // synchronous flavour: `data` (host or device) has been consumed when the call returns
+  if (h && h->weights_dirty && h->weights_stream != 0) {  // keep one upload stream at a time
+    DeviceGuard g(h->device);
+    cudaStreamSynchronize(h->weights_stream);
+  }
+  if (h) h->weights_stream = 0;
+  if (int rc = set_weight_impl(h, key, data, dtype, shape, ndim, 0)) return rc;
+  DeviceGuard g(h->device);
+  cudaError_t ce = cudaStreamSynchronize(0);
+  if (ce != cudaSuccess) return fail(h, ULLSAM_ERR_CUDA, std::string("set_weight: ") + cudaGetErrorString(ce));
+  return ULLSAM_OK;
+}
+
+int ullsam_set_weight_async(ullsam_handle* h, const char* key, const void* data, int dtype, const int64_t* shape, int ndim,
+                            void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h && h->weights_dirty && h->weights_stream != st) {  // a different upload stream than last time: drain the old one
+    DeviceGuard g(h->device);
+    cudaStreamSynchronize(h->weights_stream);
+  }
+  if (h) h->weights_stream = st;
+  return set_weight_impl(h, key, data, dtype, shape, ndim, st);
 }
 
 int ullsam_missing_weights(const ullsam_handle* h, int which) {
@@ -872,8 +940,9 @@ int ullsam_encoder_forward(ullsam_handle* h, const void* images, int dtype, int 
   if (B < 0) return fail(h, ULLSAM_ERR_INVALID, "encoder_forward: negative batch");
   if (h->cfg.depth <= 0) return fail(h, ULLSAM_ERR_STATE, "encoder_forward: this handle was created without an encoder (depth 0)");
   if (int rc = check_ready(h, 0)) return rc;
-  CKC(cudaSetDevice(h->device));
+  DEVICE_GUARD(h);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = weights_fence(h, st)) return rc;
   if (int rc = ensure_encoder_ws(h, B < kEncChunk ? B : kEncChunk)) return rc;
   const size_t img_elems = static_cast<size_t>(3) * 1024 * 1024, emb_elems = static_cast<size_t>(256) * 4096;
   for (int b0 = 0; b0 < B; b0 += kEncChunk) {
@@ -895,7 +964,8 @@ int ullsam_decoder_predict_masks(ullsam_handle* h, const void* emb, int n_img, c
                                  void* stream) {
   if (!h || !emb || !image_pe || !masks4 || !iou4 || (Ns > 0 && !sparse))
     return fail(h, ULLSAM_ERR_INVALID, "decoder: null argument");
-  CKC(cudaSetDevice(h->device));
+  DEVICE_GUARD(h);
+  if (int rc = weights_fence(h, static_cast<cudaStream_t>(stream))) return rc;
   return decoder_run(h, static_cast<const float*>(emb), n_img, static_cast<const float*>(image_pe),
                      static_cast<const float*>(sparse), P, Ns, static_cast<const float*>(dense), dense_mode, dense_batch, 0,
                      h->cfg.num_mask_tokens, static_cast<float*>(masks4), static_cast<float*>(iou4),
@@ -907,7 +977,8 @@ int ullsam_decoder_forward(ullsam_handle* h, const void* emb, int n_img, const v
                            void* stream) {
   if (!h || !emb || !image_pe || !masks || !iou || (Ns > 0 && !sparse))
     return fail(h, ULLSAM_ERR_INVALID, "decoder: null argument");
-  CKC(cudaSetDevice(h->device));
+  DEVICE_GUARD(h);
+  if (int rc = weights_fence(h, static_cast<cudaStream_t>(stream))) return rc;
   const int m0 = multimask ? 1 : 0, cnt = multimask ? h->cfg.num_mask_tokens - 1 : 1;  // mask_decoder.py:102-107
   return decoder_run(h, static_cast<const float*>(emb), n_img, static_cast<const float*>(image_pe),
                      static_cast<const float*>(sparse), P, Ns, static_cast<const float*>(dense), dense_mode, dense_batch, m0,
@@ -920,8 +991,9 @@ int ullsam_transformer_forward(ullsam_handle* h, const void* image_embedding, in
     return fail(h, ULLSAM_ERR_INVALID, "transformer: null argument");
   if (R <= 0 || Nt <= 0 || Nt > 64) return fail(h, ULLSAM_ERR_INVALID, "transformer: need 1 <= Nt <= 64 and R >= 1");
   if (int rc = check_ready(h, 1)) return rc;
-  CKC(cudaSetDevice(h->device));
+  DEVICE_GUARD(h);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = weights_fence(h, st)) return rc;
   if (int rc = ensure_decoder_ws(h, R, Nt)) return rc;
   CKC(cudaMemcpyAsync(h->tokens, point_embedding, static_cast<size_t>(R) * Nt * 256 * 4, cudaMemcpyDeviceToDevice, st));
   CKS(launch_keys_init(static_cast<const float*>(image_embedding), R, 1, nullptr, 0, 1, h->keys, h->keys_bf, st));
@@ -970,7 +1042,8 @@ int ullsam_segment_host(ullsam_handle* h, const float* images_host, int B, const
   if (int rc = check_ready(h, 0)) return rc;
   if (int rc = check_ready(h, 1)) return rc;
   if (int rc = check_ready(h, 2)) return rc;
-  CKC(cudaSetDevice(h->device));
+  DEVICE_GUARD(h);
+  if (int rc = weights_fence(h, 0)) return rc;
   const int cnt = multimask ? 3 : 1;
   const size_t img = static_cast<size_t>(3) * 1024 * 1024;
   if (B > h->host_cap_b || Ns > h->host_cap_ns) {

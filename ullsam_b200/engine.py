@@ -84,8 +84,16 @@ class Engine:
             t = t.float()
         t = t.contiguous()
         shape = (C.c_int64 * t.dim())(*t.shape)
-        check(self.lib.ullsam_set_weight(self._h, key.encode(), ptr(t), _DT[t.dtype], shape, t.dim()), self._h,
-              f"ullsam_set_weight({key})")
+        if t.is_cuda and t.device == self.device:
+            # stream-ordered upload on torch's current stream: no host sync per tensor, and a temporary made by the
+            # .float()/.contiguous() above stays valid because torch's allocator recycles it in the same stream's order
+            with torch.cuda.device(self.device):
+                rc = self.lib.ullsam_set_weight_async(self._h, key.encode(), ptr(t), _DT[t.dtype], shape, t.dim(),
+                                                      self._stream())
+            check(rc, self._h, f"ullsam_set_weight_async({key})")
+            return
+        # host tensors and tensors on another GPU: torch stages them onto the engine's device, then the same path
+        return self.set_weight(key, t.to(self.device))
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], prefixes: Iterable[Tuple[str, str]] = (("", ""),),
                         only: Optional[str] = None) -> int:

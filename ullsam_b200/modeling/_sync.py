@@ -48,9 +48,17 @@ class EngineBound:
             eng.set_weight(prefix + name, t)
             up[name] = sig
 
-    @staticmethod
-    def _check_no_grad(*tensors) -> None:
-        if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+    def _check_no_grad(self, *tensors) -> None:
+        """The kernels return tensors with no autograd graph.  Raise whenever a backward could be expected from this
+        call: grad mode on and either an input or one of THIS module's parameters requires grad — the reference's
+        training loop (train_joint_v2.py:1015-1063) feeds inputs that never require grad into modules whose parameters
+        do, so checking the inputs alone would silently stop the SAM branch from training."""
+        if not torch.is_grad_enabled():
+            return
+        if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors) or \
+                any(p.requires_grad for p in self.parameters()):
             raise _lib.UllsamError(
-                "ullsam_b200 implements the forward pass only (BASELINE north_star); call it under torch.no_grad() "
-                "or detach the inputs — there is no autograd fallback")
+                f"{type(self).__name__} (sm_100a) implements the forward pass only (BASELINE north_star): grad mode is "
+                "on and an input or a parameter of this module requires grad, so a backward would be expected and "
+                "there is none (no autograd fallback).  Call it under torch.no_grad() / torch.inference_mode(), or "
+                "freeze the module with .requires_grad_(False) and detach the inputs")

@@ -90,8 +90,13 @@ class PromptEncoder(nn.Module):
         if masks is not None:
             raise _lib.UllsamError("PromptEncoder (sm_100a): mask prompts (mask_downscaling) are not on uLLSAM's path "
                                    "and are not implemented; pass masks=None")
-        if torch.is_grad_enabled() and llm_hidden_states is not None and llm_hidden_states.requires_grad:
-            raise _lib.UllsamError("PromptEncoder (sm_100a) is forward-only; call it under torch.no_grad()")
+        # forward only: the same rule as the encoder / decoder shims (ullsam_b200/modeling/_sync.py) — with grad mode on,
+        # llm_scale_factor / llm_bias / the point embeddings requiring grad means a backward is expected
+        if torch.is_grad_enabled() and (
+                (llm_hidden_states is not None and llm_hidden_states.requires_grad)
+                or any(p.requires_grad for p in self.parameters())):
+            raise _lib.UllsamError("PromptEncoder (sm_100a) is forward-only: grad mode is on and an input or a parameter "
+                                   "requires grad; call it under torch.no_grad() or freeze it with .requires_grad_(False)")
         g = self._gauss()
         dev = self._get_device()
         if points is not None:

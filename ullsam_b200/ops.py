@@ -14,12 +14,35 @@ from . import _lib
 from ._lib import GemmDesc, check, current_stream_ptr, ptr
 
 
+import functools
+
+
 def _require_cuda(*tensors) -> None:
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise _lib.UllsamError("ullsam_b200 ops need CUDA tensors; there is no CPU path")
 
 
+def _on_tensor_device(fn):
+    """The op-level ABI launches on the CURRENT device and takes only the stream from the tensor's device: make the
+    device of the first tensor argument current for the duration of the call (tensors on a non-current GPU would
+    otherwise fail with an invalid resource handle), and restore the caller's device afterwards."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        first = next((a for a in list(args) + list(kwargs.values()) if isinstance(a, torch.Tensor)), None)
+        if first is None or not first.is_cuda:
+            return fn(*args, **kwargs)   # the op raises its own "no CPU path" error
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda and a.device != first.device:
+                raise _lib.UllsamError(f"{fn.__name__}: tensors on different devices ({first.device} vs {a.device})")
+        with torch.cuda.device(first.device):
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
+@_on_tensor_device
 def gemm(
     a: torch.Tensor,
     w: torch.Tensor,
@@ -79,6 +102,7 @@ def gemm(
     return out
 
 
+@_on_tensor_device
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, window: int = 0) -> torch.Tensor:
     """x fp32 [B, grid, grid, dim] -> bf16 LayerNorm; ``window`` > 0 also window-partitions (zero pad rows)."""
     _require_cuda(x, gamma, beta)
@@ -105,6 +129,7 @@ def pad_rel_table(rel: torch.Tensor, grid: int) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor,
               grid: int) -> torch.Tensor:
     """q,k,v bf16 [G, heads, grid*grid, 64]; rel_h/rel_w fp32 [2*grid-1, 64] (the module parameters).
@@ -124,6 +149,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, rel_h: torch.Te
     return out
 
 
+@_on_tensor_device
 def im2col(images: torch.Tensor) -> torch.Tensor:
     _require_cuda(images)
     B = images.shape[0]
@@ -135,6 +161,7 @@ def im2col(images: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     _require_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous()
@@ -146,6 +173,7 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
 
 # ---- PromptEncoder (the step upstream of the decoder) ---------------------------------------------------------------
 
+@_on_tensor_device
 def prompt_dense_pe(gauss: torch.Tensor, grid: int) -> torch.Tensor:
     """PositionEmbeddingRandom.forward((grid, grid)) (prompt_encoder.py:230-241): gauss [2, F] -> [2F, grid, grid]."""
     _require_cuda(gauss)
@@ -157,6 +185,7 @@ def prompt_dense_pe(gauss: torch.Tensor, grid: int) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def prompt_sparse(gauss: torch.Tensor, point_emb: torch.Tensor, not_a_point: torch.Tensor,
                   coords: Optional[torch.Tensor], labels: Optional[torch.Tensor], boxes: Optional[torch.Tensor],
                   pad: bool, img_w: float, img_h: float) -> torch.Tensor:
@@ -178,6 +207,7 @@ def prompt_sparse(gauss: torch.Tensor, point_emb: torch.Tensor, not_a_point: tor
     return out
 
 
+@_on_tensor_device
 def prompt_llm_dense(x: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """_normalize_llm_hidden_states (prompt_encoder.py:131-151): x [P, C, H, W] fp32/bf16 -> fp32, same shape."""
     _require_cuda(x, scale, bias)
@@ -187,14 +217,19 @@ def prompt_llm_dense(x: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor) -
     P, Cc, H, W = x.shape
     dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}[x.dtype]
     out = torch.empty((P, Cc, H, W), dtype=torch.float32, device=x.device)
-    check(_lib.load().ullsam_op_prompt_llm_dense(ptr(x), dt, P, Cc, H * W, ptr(scale.float().contiguous()),
-                                                 ptr(bias.float().contiguous()), ptr(out), current_stream_ptr(x.device)),
+    # the converted copies must outlive the launch: a temporary passed straight to ptr() is freed (and its block handed
+    # to the next temporary by the caching allocator) before the kernel reads it
+    s = scale.detach().float().contiguous()
+    b = bias.detach().float().contiguous()
+    check(_lib.load().ullsam_op_prompt_llm_dense(ptr(x), dt, P, Cc, H * W, ptr(s), ptr(b), ptr(out),
+                                                 current_stream_ptr(x.device)),
           what="ullsam_op_prompt_llm_dense")
     return out
 
 
 # ---- MLLM bridge ------------------------------------------------------------------------------------------------------
 
+@_on_tensor_device
 def pixel_shuffle(x: torch.Tensor, to_tokens: bool, ps_version: str = "v2") -> torch.Tensor:
     """InternVL pixel shuffle with ratio 0.5 (modeling_internvl_sam.py:211-270): emb fp32 [B,256,64,64] -> tokens
     [B,1024,1024] (``to_tokens``) or back."""

@@ -25,13 +25,29 @@ def shard_sizes(n_items: int, world: int) -> List[int]:
     return [shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world)]
 
 
-def gather_batch(local: torch.Tensor, n_items: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+def gather_batch(local: Optional[torch.Tensor], n_items: int, group: Optional[dist.ProcessGroup] = None,
+                 device: Optional[torch.device] = None) -> torch.Tensor:
     """All-gather per-rank shards (dim 0 sized by ``shard_range``) back into the full batch, in rank order.
-    Equal shards use one ``all_gather_into_tensor``; ragged shards are padded to the largest one first."""
+    Equal shards use one ``all_gather_into_tensor``; ragged shards are padded to the largest one first.
+
+    A rank whose shard is empty (``n_items < world``) may pass ``local=None``: it has run no kernel and does not know
+    the item shape, so the ranks first agree on (trailing shape, dtype) with a small object all-gather — every rank
+    takes that branch together because ``shard_sizes`` is a pure function of (n_items, world)."""
     if not (dist.is_available() and dist.is_initialized()):
+        if local is None:
+            raise ValueError("gather_batch: an empty shard needs a process group to learn the item shape from")
         return local
     world = dist.get_world_size(group)
     sizes = shard_sizes(n_items, world)
+    if min(sizes) == 0:
+        meta = [None] * world
+        dist.all_gather_object(meta, None if local is None else (tuple(local.shape[1:]), local.dtype), group=group)
+        known = next((m for m in meta if m is not None), None)
+        if known is None:
+            raise ValueError("gather_batch: every shard is empty")
+        if local is None:
+            dev = device if device is not None else torch.device("cpu")
+            local = torch.empty((0,) + known[0], dtype=known[1], device=dev)
     if local.shape[0] != sizes[dist.get_rank(group)]:
         raise ValueError(f"rank {dist.get_rank(group)} holds {local.shape[0]} items, expected {sizes[dist.get_rank(group)]}")
     mx = max(sizes)
@@ -56,11 +72,16 @@ def segment_sharded(engine, images: torch.Tensor, image_pe: torch.Tensor, sparse
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     lo, hi = shard_range(n, rank, world)
     dev = engine.device
-    emb = engine.encoder_forward(images[lo:hi].to(dev, non_blocking=True))
-    d = dense if dense.shape[0] == 1 else dense[lo:hi]
-    masks, iou = engine.decoder_forward(emb, image_pe.to(dev), sparse[lo:hi].to(dev), d.to(dev), multimask_output,
-                                        prompts_per_image=1)
-    out = (gather_batch(masks, n, group), gather_batch(iou, n, group))
+    if hi > lo:
+        emb = engine.encoder_forward(images[lo:hi].to(dev, non_blocking=True))
+        d = dense if dense.shape[0] == 1 else dense[lo:hi]
+        masks, iou = engine.decoder_forward(emb, image_pe.to(dev), sparse[lo:hi].to(dev), d.to(dev), multimask_output,
+                                            prompts_per_image=1)
+    else:
+        # fewer images than ranks: this rank has nothing to encode (the decoder rejects an empty batch), but it still
+        # has to join every collective the other ranks enter, or they hang
+        emb = masks = iou = None
+    out = (gather_batch(masks, n, group, dev), gather_batch(iou, n, group, dev))
     if gather_embeddings:
-        out = out + (gather_batch(emb, n, group),)
+        out = out + (gather_batch(emb, n, group, dev),)
     return out

@@ -14,9 +14,10 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from .ops import _require_cuda, check, current_stream_ptr, ptr
+from .ops import _on_tensor_device, _require_cuda, check, current_stream_ptr, ptr
 
 
+@_on_tensor_device
 def resize_masks(masks: torch.Tensor, size: Tuple[int, int], crop: Optional[Tuple[int, int]] = None,
                  threshold: Optional[float] = None, return_logits: bool = True
                  ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
@@ -47,6 +48,7 @@ def postprocess_masks(masks: torch.Tensor, input_size: Tuple[int, ...], original
     return out
 
 
+@_on_tensor_device
 def mask_iou(logits: torch.Tensor, target: torch.Tensor, threshold: float = 0.0, smooth: float = 1e-7) -> torch.Tensor:
     """``CalcIoU`` (train_joint_v2.py:666-696): logits, target [B, N, H, W] -> IoU [B, N] of (sigmoid > 0.5) vs target."""
     _require_cuda(logits, target)
