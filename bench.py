@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
-    ap.add_argument("--model", default="vit_b", choices=["vit_b", "vit_l", "vit_h"])
+    ap.add_argument("--model", default="vit_b", choices=["vit_b", "vit_l"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

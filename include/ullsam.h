@@ -46,8 +46,8 @@ typedef struct {
   int32_t img_size;      /* 1024 */
   int32_t patch_size;    /* 16   */
   int32_t in_chans;      /* 3    */
-  int32_t embed_dim;     /* 768 (vit_b) / 1024 (vit_l) / 1280 (vit_h); multiple of 64 */
-  int32_t depth;         /* 12 / 24 / 32 */
+  int32_t embed_dim;     /* 768 (vit_b) / 1024 (vit_l); vit_h (1280, 80-wide heads) is rejected by ullsam_create */
+  int32_t depth;         /* 12 / 24 (0: decoder-only handle) */
   int32_t num_heads;     /* embed_dim / 64 */
   int32_t mlp_dim;       /* embed_dim * mlp_ratio */
   int32_t out_chans;     /* 256 */
@@ -220,6 +220,14 @@ int ullsam_op_prompt_sparse(const float* gauss, int F, const float* point_emb, c
  * -> out fp32 [P, C, HW] = layer_norm over C (no affine, eps 1e-5) * llm_scale_factor[0] + llm_bias[0]. */
 int ullsam_op_prompt_llm_dense(const void* x, int dtype, int P, int C, int HW, const float* scale, const float* bias,
                                float* out, void* stream);
+
+/* PromptEncoder._embed_masks == mask_downscaling (prompt_encoder.py:53-61, 105-108, 176-177): the mask-prompt branch of
+ * stock SAM (Sam.forward feeds low-res mask inputs here, sam.py:106-110; uLLSAM itself passes masks=None).
+ * masks fp32 [P, 1, 4G, 4G] -> out fp32 [P, E, G, G].  params = the 10 fp32 device tensors of mask_downscaling in
+ * state_dict order: 0.weight [c1,1,2,2], 0.bias, 1.weight, 1.bias (LayerNorm2d c1), 3.weight [c2,c1,2,2], 3.bias,
+ * 4.weight, 4.bias (LayerNorm2d c2), 6.weight [E,c2,1,1], 6.bias.  c1 <= 8, c2 <= 32 (SAM: 4, 16, E = 256, G = 64). */
+int ullsam_op_prompt_mask_embed(const float* masks, int P, int G, int c1, int c2, int E, const float* const* params,
+                                float* out, void* stream);
 
 /* ---- mask post-processing (the step downstream of the decoder) ---------------------- */
 

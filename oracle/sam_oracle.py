@@ -218,6 +218,18 @@ def dense_from_llm(sd: SD, llm_map: torch.Tensor, prefix: str = "prompt_encoder.
     return n * sd[prefix + "llm_scale_factor"] + sd[prefix + "llm_bias"]
 
 
+def embed_masks(sd: SD, masks: torch.Tensor, prefix: str = "prompt_encoder.") -> torch.Tensor:
+    """Stock SAM's mask-prompt branch, prompt_encoder.py:53-61, 105-108, 176-177 (mask_downscaling):
+    Conv2d(1, c/4, k2, s2) -> LayerNorm2d -> GELU -> Conv2d(c/4, c, k2, s2) -> LayerNorm2d -> GELU -> Conv2d(c, E, 1).
+    masks [P, 1, 256, 256] -> [P, 256, 64, 64]."""
+    p = prefix + "mask_downscaling."
+    x = F.conv2d(masks, sd[p + "0.weight"], sd[p + "0.bias"], stride=2)
+    x = gelu(layer_norm_2d(x, sd[p + "1.weight"], sd[p + "1.bias"]))
+    x = F.conv2d(x, sd[p + "3.weight"], sd[p + "3.bias"], stride=2)
+    x = gelu(layer_norm_2d(x, sd[p + "4.weight"], sd[p + "4.bias"]))
+    return F.conv2d(x, sd[p + "6.weight"], sd[p + "6.bias"])
+
+
 # =====================================================================================================
 # decoder
 # =====================================================================================================

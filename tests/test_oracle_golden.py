@@ -142,3 +142,30 @@ def test_postprocess_restatement_vs_reference_golden():
     logits = torch.nn.functional.interpolate(low_res(40), (512, 512), mode="bilinear", align_corners=False)
     target = (torch.nn.functional.interpolate(low_res(41), (512, 512), mode="bilinear", align_corners=False) > 0.5).float()
     assert np.allclose(O.calc_iou(logits, target).numpy(), g["iou"], atol=1e-7)
+
+
+def test_mask_prompt_branch_vs_reference_golden():
+    """oracle embed_masks (stock SAM's mask_downscaling, prompt_encoder.py:53-61, 105-108) and the decoder fed with it,
+    against the reference's own PromptEncoder / MaskDecoder (oracle/make_golden_prompt_mask.py)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import sam_oracle as O
+    from oracle.make_golden_prompt_mask import make_mask_inputs
+    from ullsam_b200 import synth
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "prompt_mask.npz"))
+    seed, P = int(g["seed"]), int(g["P"])
+    cfg = O.config("vit_b")
+    sd = synth.make_state_dict(cfg, seed)
+    masks_in = make_mask_inputs(P, seed + 21)
+    _, boxes = synth.make_images(P, 1024, seed=seed + 1)
+    with torch.no_grad():
+        dense = O.embed_masks(sd, masks_in)
+        assert dense.shape == (P, 256, 64, 64)
+        assert np.abs(dense[:, :, ::4, ::4].numpy() - g["dense"]).max() < 1e-5
+        sparse = O.embed_boxes(sd, boxes, cfg)
+        assert np.abs(sparse.numpy() - g["sparse"]).max() < 1e-5
+        emb = torch.randn(1, 256, 64, 64, generator=torch.Generator().manual_seed(seed + 22)) * 0.5
+        m, s = O.decoder_forward(sd, emb, O.dense_pe(sd, cfg), sparse, dense, True, cfg)
+        assert np.abs(m[:, :, ::4, ::4].numpy() - g["masks"]).max() < 2e-3 and np.abs(s.numpy() - g["iou"]).max() < 2e-4

@@ -156,11 +156,45 @@ def test_accelerate_swaps_the_prompt_encoder_of_a_built_model(ctx):
     assert torch.equal(a, b)
 
 
+def test_mask_prompt_branch_vs_reference_golden_and_oracle(ctx):
+    """Stock SAM's mask prompts (mask_downscaling, prompt_encoder.py:53-61, 105-108, 176-177) as one fused kernel: against
+    the reference-generated golden (oracle/make_golden_prompt_mask.py) and the oracle, then through the CUDA decoder with
+    multimask output (the Sam.forward combination of a box and a mask prompt, sam.py:101-117)."""
+    from oracle.make_golden_prompt_mask import make_mask_inputs
+    from ullsam_b200.engine import Engine
+
+    g = np.load(os.path.join(GOLD, "prompt_mask.npz"))
+    seed, P = int(g["seed"]), int(g["P"])
+    assert seed == ctx["seed"]
+    masks_in = make_mask_inputs(P, seed + 21)
+    _, boxes = synth.make_images(P, 1024, seed=seed + 1)
+    with torch.no_grad():
+        sparse, dense = ctx["pe"](points=None, boxes=boxes.cuda(), masks=masks_in.cuda())
+    assert dense.shape == (P, 256, 64, 64) and sparse.shape == (P, 2, 256)
+    _close(dense[:, :, ::4, ::4], g["dense"], 2e-5, "mask-prompt dense embedding vs reference golden")
+    _close(dense, O.embed_masks(ctx["sd"], masks_in), 2e-5, "mask-prompt dense embedding vs oracle")
+    eng = Engine(model="vit_b")
+    eng.load_state_dict(ctx["sd"])
+    emb = torch.randn(1, 256, 64, 64, generator=torch.Generator().manual_seed(seed + 22)) * 0.5
+    with torch.no_grad():
+        m, s = eng.decoder_forward(emb.cuda(), ctx["pe"].get_dense_pe(), sparse, dense, multimask_output=True)
+    ref = torch.from_numpy(g["masks"])
+    a, b = m[:, :, ::4, ::4].cpu() > 0, ref > 0
+    iou = (a & b).sum().item() / max((a | b).sum().item(), 1)
+    print(f"mask-prompt decoder: binarised IoU vs reference golden {iou:.4f}, iou-head err {(s.cpu() - torch.from_numpy(g['iou'])).abs().max().item():.2e}")
+    assert iou >= 0.99
+    eng.close()
+
+
 def test_errors_are_loud(ctx):
     from ullsam_b200 import _lib
 
-    with pytest.raises(_lib.UllsamError):
-        ctx["pe"](points=None, boxes=None, masks=torch.zeros(1, 1, 256, 256, device="cuda"))
+    with torch.no_grad(), pytest.raises(_lib.UllsamError, match="mask prompts must be"):
+        ctx["pe"](points=None, boxes=None, masks=torch.zeros(1, 1, 128, 128, device="cuda"))   # wrong mask_input_size
+    import copy
+    trainable = copy.deepcopy(ctx["pe"]).requires_grad_(True)
+    with pytest.raises(_lib.UllsamError, match="forward-only"):      # grad mode on + trainable parameters
+        trainable(points=None, boxes=torch.tensor([[1.0, 2.0, 30.0, 40.0]], device="cuda"), masks=None)
     from ullsam_b200.modeling import PromptEncoder
     cpu = PromptEncoder(256, (64, 64), (1024, 1024), 16)
     with pytest.raises(_lib.UllsamError):

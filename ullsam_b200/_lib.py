@@ -143,6 +143,8 @@ PROTOTYPES = {
         [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
          C.c_float, C.c_float, C.c_void_p, C.c_void_p],
     ),
+    "ullsam_op_prompt_mask_embed": (
+        C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "ullsam_op_prompt_llm_dense": (
         C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -42,13 +42,13 @@ class SamConfig:
 
 
 def config(name: str) -> SamConfig:
-    """build_sam.py:14-44 (vit_h / vit_l / vit_b) plus a tiny configuration used to pin the oracle cheaply."""
+    """build_sam.py:24-44 (vit_l / vit_b) plus a tiny configuration used to pin the oracle cheaply.  vit_h
+    (build_sam.py:14-21: 1280 / 16 heads = 80-wide heads) is NOT supported: the attention kernels are specialised for
+    64-wide heads, and uLLSAM itself only ships ViT-B (build_sam.py:50-52 registry, train_joint_v2.py:1365)."""
     if name == "vit_b":
         return SamConfig()
     if name == "vit_l":
         return SamConfig(name="vit_l", embed_dim=1024, depth=24, num_heads=16, global_attn_indexes=(5, 11, 17, 23))
-    if name == "vit_h":
-        return SamConfig(name="vit_h", embed_dim=1280, depth=32, num_heads=16, global_attn_indexes=(7, 15, 23, 31))
     if name == "tiny":
         # 20x20 token grid: windows of 14 need padding to 28 (edge windows are partly padding), one global block.
         return SamConfig(name="tiny", img_size=320, embed_dim=128, depth=3, num_heads=2, global_attn_indexes=(1,),

@@ -110,6 +110,18 @@ int ullsam_op_prompt_llm_dense(const void* x, int dtype, int P, int C, int HW, c
   return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
 }
 
+int ullsam_op_prompt_mask_embed(const float* masks, int P, int G, int c1, int c2, int E, const float* const* params, float* out,
+                                void* stream) {
+  if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_prompt_mask_embed: no sm_100 device");
+  if (!masks || !params || !out) return op_fail(ULLSAM_ERR_INVALID, "op_prompt_mask_embed: null argument");
+  for (int i = 0; i < 10; ++i)
+    if (!params[i]) return op_fail(ULLSAM_ERR_INVALID, "op_prompt_mask_embed: null parameter tensor");
+  const char* e = launch_prompt_mask_downscale(masks, P, G, c1, c2, E, params[0], params[1], params[2], params[3], params[4],
+                                               params[5], params[6], params[7], params[8], params[9], out,
+                                               static_cast<cudaStream_t>(stream));
+  return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
+}
+
 int ullsam_op_pixel_shuffle(const float* in, int B, int v1, int to_tokens, float* out, void* stream) {
   if (device_sm_count() <= 0) return op_fail(ULLSAM_ERR_NO_DEVICE, "op_pixel_shuffle: no sm_100 device");
   const char* e = launch_pixel_shuffle(in, B, v1, to_tokens, out, static_cast<cudaStream_t>(stream));

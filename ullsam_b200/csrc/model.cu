@@ -798,8 +798,8 @@ int ullsam_create(const ullsam_config* cfg, int device, ullsam_handle** out) {
     return fail(nullptr, ULLSAM_ERR_NO_DEVICE, "create: device is not sm_100 (B200); the kernels are sm_100a-only");
   if (cfg->img_size != 1024 || cfg->patch_size != 16 || cfg->in_chans != 3 || cfg->window_size != 14 || cfg->out_chans != 256)
     return fail(nullptr, ULLSAM_ERR_INVALID, "create: kernels are specialised for img 1024 / patch 16 / window 14 / out 256");
-  if (cfg->embed_dim != cfg->num_heads * 64 || (cfg->embed_dim != 768 && cfg->embed_dim != 1024 && cfg->embed_dim != 1280))
-    return fail(nullptr, ULLSAM_ERR_INVALID, "create: embed_dim must be 768/1024/1280 with 64-wide heads");
+  if (cfg->depth > 0 && (cfg->embed_dim != cfg->num_heads * 64 || (cfg->embed_dim != 768 && cfg->embed_dim != 1024)))
+    return fail(nullptr, ULLSAM_ERR_INVALID, "create: embed_dim must be 768 (vit_b) or 1024 (vit_l) with 64-wide heads; vit_h (80-wide heads) is not implemented");
   if (cfg->mlp_dim % 256 != 0 || cfg->depth < 0 || cfg->num_global < 0 || cfg->num_global > 8)
     return fail(nullptr, ULLSAM_ERR_INVALID, "create: bad mlp_dim / global_attn_indexes");
   if (cfg->transformer_dim != 256 || cfg->dec_heads != 8 || cfg->num_mask_tokens != 4 || cfg->dec_mlp_dim % 4 != 0 ||

@@ -113,7 +113,103 @@ __global__ void __launch_bounds__(256) llm_dense_kernel(const T* __restrict__ x,
   }
 }
 
+
+// PromptEncoder._embed_masks == mask_downscaling (prompt_encoder.py:53-61, 105-108):
+//   Conv2d(1, c1, k2, s2) -> LayerNorm2d(c1) -> GELU -> Conv2d(c1, c2, k2, s2) -> LayerNorm2d(c2) -> GELU -> Conv2d(c2, E, 1)
+// One CTA per (output row, mask): a 4x4 input patch feeds one output pixel, so the two strided convolutions, both
+// channel LayerNorms (eps 1e-6, biased variance, common.py:31-43) and both exact-erf GELUs are computed per pixel in
+// registers by the first G threads; then every thread owns output channels and streams E x G fp32 out, 16 bytes at a time.
+template <int C1MAX, int C2MAX>
+__global__ void __launch_bounds__(256) mask_downscale_kernel(const float* __restrict__ masks, int G, int c1, int c2, int E,
+                                                             const float* __restrict__ w0, const float* __restrict__ b0,
+                                                             const float* __restrict__ g1, const float* __restrict__ be1,
+                                                             const float* __restrict__ w3, const float* __restrict__ b3,
+                                                             const float* __restrict__ g4, const float* __restrict__ be4,
+                                                             const float* __restrict__ w6, const float* __restrict__ b6,
+                                                             float* __restrict__ out) {
+  extern __shared__ float feat[];   // [c2][G]
+  const int oy = blockIdx.x, p = blockIdx.y;
+  const int W = 4 * G;
+  for (int ox = threadIdx.x; ox < G; ox += blockDim.x) {
+    const float* src = masks + (static_cast<size_t>(p) * W + 4 * oy) * W + 4 * ox;
+    float in[4][4];
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const float4 v = *reinterpret_cast<const float4*>(src + static_cast<size_t>(y) * W);
+      in[y][0] = v.x; in[y][1] = v.y; in[y][2] = v.z; in[y][3] = v.w;
+    }
+    float h1[2][2][C1MAX];   // stage-1 features at the 2x2 positions of the patch
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        float mean = 0.f;
+        for (int c = 0; c < c1; ++c) {
+          float a = b0[c];
+#pragma unroll
+          for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 2; ++kx) a = fmaf(w0[(c * 2 + ky) * 2 + kx], in[2 * py + ky][2 * px + kx], a);
+          h1[py][px][c] = a;
+          mean += a;
+        }
+        mean /= c1;
+        float var = 0.f;
+        for (int c = 0; c < c1; ++c) { const float d = h1[py][px][c] - mean; var = fmaf(d, d, var); }
+        const float rstd = 1.0f / sqrtf(var / c1 + 1e-6f);
+        for (int c = 0; c < c1; ++c) {
+          const float x = (h1[py][px][c] - mean) * rstd * g1[c] + be1[c];
+          h1[py][px][c] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+        }
+      }
+    float h2[C2MAX];
+    float mean = 0.f;
+    for (int o = 0; o < c2; ++o) {
+      float a = b3[o];
+      for (int c = 0; c < c1; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 2; ++kx) a = fmaf(w3[((o * c1 + c) * 2 + ky) * 2 + kx], h1[ky][kx][c], a);
+      h2[o] = a;
+      mean += a;
+    }
+    mean /= c2;
+    float var = 0.f;
+    for (int o = 0; o < c2; ++o) { const float d = h2[o] - mean; var = fmaf(d, d, var); }
+    const float rstd = 1.0f / sqrtf(var / c2 + 1e-6f);
+    for (int o = 0; o < c2; ++o) {
+      const float x = (h2[o] - mean) * rstd * g4[o] + be4[o];
+      feat[o * G + ox] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    }
+  }
+  __syncthreads();
+  // 1x1 convolution to E channels: thread -> (channel, group of 4 pixels)
+  const int groups = G / 4;
+  for (int i = threadIdx.x; i < E * groups; i += blockDim.x) {
+    const int e = i / groups, x4 = (i % groups) * 4;
+    const float bias = b6[e];
+    float4 acc = make_float4(bias, bias, bias, bias);
+    for (int o = 0; o < c2; ++o) {
+      const float w = w6[e * c2 + o];
+      const float4 f = *reinterpret_cast<const float4*>(feat + o * G + x4);
+      acc.x = fmaf(w, f.x, acc.x); acc.y = fmaf(w, f.y, acc.y); acc.z = fmaf(w, f.z, acc.z); acc.w = fmaf(w, f.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(out + ((static_cast<size_t>(p) * E + e) * G + oy) * G + x4) = acc;
+  }
+}
+
 }  // namespace
+
+const char* launch_prompt_mask_downscale(const float* masks, int P, int G, int c1, int c2, int E, const float* w0, const float* b0,
+                                         const float* g1, const float* be1, const float* w3, const float* b3, const float* g4,
+                                         const float* be4, const float* w6, const float* b6, float* out, cudaStream_t stream) {
+  if (P <= 0) return nullptr;
+  if (c1 <= 0 || c1 > 8 || c2 <= 0 || c2 > 32 || G % 4 != 0 || G <= 0 || E <= 0) return "prompt: mask_downscaling sizes out of range (c1 <= 8, c2 <= 32, grid % 4 == 0)";
+  mask_downscale_kernel<8, 32><<<dim3(G, P), 256, static_cast<size_t>(c2) * G * sizeof(float), stream>>>(
+      masks, G, c1, c2, E, w0, b0, g1, be1, w3, b3, g4, be4, w6, b6, out);
+  return last_err();
+}
 
 const char* launch_prompt_pe_grid(const float* gauss, int F, int g, float* out, cudaStream_t stream) {
   if (F <= 0 || g <= 0) return "prompt: bad positional-encoding size";

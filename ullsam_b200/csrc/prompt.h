@@ -21,4 +21,10 @@ const char* launch_prompt_sparse(const float* gauss, int F, const float* point_e
 const char* launch_prompt_llm_dense(const void* x, int is_bf16, int P, int C, int HW, const float* scale, const float* bias,
                                     float* out, cudaStream_t stream);
 
+// PromptEncoder._embed_masks == mask_downscaling (prompt_encoder.py:53-61, 105-108): masks [P][1][4G][4G] fp32 ->
+// out [P][E][G][G] fp32.  w0 [c1][1][2][2], w3 [c2][c1][2][2], w6 [E][c2][1][1]; g*/be* are the LayerNorm2d weight / bias.
+const char* launch_prompt_mask_downscale(const float* masks, int P, int G, int c1, int c2, int E, const float* w0, const float* b0,
+                                         const float* g1, const float* be1, const float* w3, const float* b3, const float* g4,
+                                         const float* be4, const float* w6, const float* b6, float* out, cudaStream_t stream);
+
 }  // namespace ullsam

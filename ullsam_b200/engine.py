@@ -43,7 +43,7 @@ MODEL_CONFIGS = {
     # build_sam.py:14-44
     "vit_b": dict(embed_dim=768, depth=12, num_heads=12, global_attn_indexes=(2, 5, 8, 11)),
     "vit_l": dict(embed_dim=1024, depth=24, num_heads=16, global_attn_indexes=(5, 11, 17, 23)),
-    "vit_h": dict(embed_dim=1280, depth=32, num_heads=16, global_attn_indexes=(7, 15, 23, 31)),
+    # vit_h (1280 / 16 = 80-wide heads) is not supported: the attention kernels are built for 64-wide heads
 }
 
 

@@ -69,7 +69,9 @@ class ImageEncoderViT(EngineBound, nn.Module):
         # The kernels are specialised for the configuration build_sam.py fixes (build_sam.py:62-81).
         unsupported = []
         if img_size != 1024 or patch_size != 16 or in_chans != 3: unsupported.append("img_size/patch_size/in_chans != 1024/16/3")
-        if embed_dim // max(num_heads, 1) != 64 or embed_dim not in (768, 1024, 1280): unsupported.append("embed_dim/num_heads")
+        if embed_dim != 64 * num_heads or embed_dim not in (768, 1024):
+            unsupported.append("embed_dim/num_heads (64-wide heads with embed_dim 768 = vit_b or 1024 = vit_l; vit_h's "
+                               "80-wide heads are not implemented)")
         if out_chans != 256: unsupported.append("out_chans != 256")
         if not (qkv_bias and use_abs_pos and use_rel_pos): unsupported.append("qkv_bias/use_abs_pos/use_rel_pos must be True")
         if window_size != 14: unsupported.append("window_size != 14")

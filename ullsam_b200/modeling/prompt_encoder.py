@@ -9,8 +9,9 @@ Same constructor, attributes (``embed_dim``, ``input_image_size``, ``image_embed
 ~20 tiny eager launches and its boolean-mask indexing (a host sync per call) are gone.  ``get_dense_pe`` is cached: it
 only depends on a buffer.
 
-Not on uLLSAM's path and therefore not implemented: the mask-prompt branch (``masks is not None``,
-``mask_downscaling``) — the parameters exist so that checkpoints load, the call raises.
+The mask-prompt branch of stock SAM (``masks is not None`` -> ``mask_downscaling``, prompt_encoder.py:105-108, 176-177;
+uLLSAM itself always passes ``masks=None``) is one fused kernel (``ullsam_op_prompt_mask_embed``), so the class is a
+complete drop-in for ``Sam.forward`` (sam.py:106-110) as well.
 """
 from __future__ import annotations
 
@@ -87,9 +88,6 @@ class PromptEncoder(nn.Module):
                 masks: Optional[torch.Tensor], llm_hidden_states: Optional[torch.Tensor] = None
                 ) -> Tuple[torch.Tensor, torch.Tensor]:
         """prompt_encoder.py:153-203: -> (sparse [B, N, embed_dim], dense [B, embed_dim, H, W])."""
-        if masks is not None:
-            raise _lib.UllsamError("PromptEncoder (sm_100a): mask prompts (mask_downscaling) are not on uLLSAM's path "
-                                   "and are not implemented; pass masks=None")
         # forward only: the same rule as the encoder / decoder shims (ullsam_b200/modeling/_sync.py) — with grad mode on,
         # llm_scale_factor / llm_bias / the point embeddings requiring grad means a backward is expected
         if torch.is_grad_enabled() and (
@@ -99,10 +97,12 @@ class PromptEncoder(nn.Module):
                                    "requires grad; call it under torch.no_grad() or freeze it with .requires_grad_(False)")
         g = self._gauss()
         dev = self._get_device()
-        if points is not None:
+        if points is not None:                       # _get_batch_size, prompt_encoder.py:110-125
             bs = points[0].shape[0]
         elif boxes is not None:
             bs = boxes.shape[0]
+        elif masks is not None:
+            bs = masks.shape[0]
         else:
             bs = 1
         if points is None and boxes is None:
@@ -113,7 +113,14 @@ class PromptEncoder(nn.Module):
             sparse = ops.prompt_sparse(g, pe, self.not_a_point_embed.weight.detach(), coords, labels, boxes,
                                        pad=(boxes is None), img_w=self.input_image_size[1], img_h=self.input_image_size[0])
         H, W = self.image_embedding_size
-        if llm_hidden_states is not None:
+        if masks is not None:                        # takes precedence over the LLM map, as in the reference (:176-177)
+            if tuple(masks.shape[-2:]) != tuple(self.mask_input_size):
+                raise _lib.UllsamError(f"PromptEncoder (sm_100a): mask prompts must be {self.mask_input_size}, got "
+                                       f"{tuple(masks.shape[-2:])}")
+            md = self.mask_downscaling
+            dense = ops.prompt_mask_embed(masks, [md[0].weight, md[0].bias, md[1].weight, md[1].bias, md[3].weight, md[3].bias,
+                                                  md[4].weight, md[4].bias, md[6].weight, md[6].bias])
+        elif llm_hidden_states is not None:
             dense = self._normalize_llm_hidden_states(llm_hidden_states).reshape(bs, -1, H, W)
         else:
             dense = self.no_mask_embed.weight.detach().reshape(1, -1, 1, 1).expand(bs, -1, H, W)

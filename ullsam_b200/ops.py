@@ -227,6 +227,27 @@ def prompt_llm_dense(x: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor) -
     return out
 
 
+@_on_tensor_device
+def prompt_mask_embed(masks: torch.Tensor, params) -> torch.Tensor:
+    """_embed_masks / mask_downscaling (prompt_encoder.py:53-61, 105-108): masks [P, 1, 4G, 4G] -> fp32 [P, E, G, G].
+    ``params``: the 10 tensors of ``mask_downscaling`` in state_dict order."""
+    _require_cuda(masks, *params)
+    if len(params) != 10:
+        raise _lib.UllsamError("prompt_mask_embed: expected the 10 tensors of mask_downscaling")
+    x = masks.float().contiguous()
+    P, one, H, W = x.shape
+    if one != 1 or H != W or H % 16 != 0:
+        raise _lib.UllsamError(f"prompt_mask_embed: expected [P, 1, 4G, 4G] with G % 4 == 0, got {tuple(masks.shape)}")
+    G = H // 4
+    ps = [t.detach().float().contiguous() for t in params]     # kept alive until the launch has been queued
+    c1, c2, E = ps[0].shape[0], ps[4].shape[0], ps[8].shape[0]
+    arr = (C.c_void_p * 10)(*[ptr(t) for t in ps])
+    out = torch.empty((P, E, G, G), dtype=torch.float32, device=x.device)
+    check(_lib.load().ullsam_op_prompt_mask_embed(ptr(x), P, G, c1, c2, E, arr, ptr(out), current_stream_ptr(x.device)),
+          what="ullsam_op_prompt_mask_embed")
+    return out
+
+
 # ---- MLLM bridge ------------------------------------------------------------------------------------------------------
 
 @_on_tensor_device
