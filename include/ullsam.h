@@ -127,9 +127,12 @@ int ullsam_decoder_predict_masks(ullsam_handle* h, const void* emb, int n_img, c
 int ullsam_transformer_forward(ullsam_handle* h, const void* image_embedding, int R, const void* image_pe,
                                const void* point_embedding, int Nt, void* queries, void* keys, void* stream);
 
-/* End-to-end with HOST buffers (pinned or pageable): H2D of the images and prompts, encoder,
- * decoder (one prompt set per image), D2H of masks / iou / optionally embeddings; synchronises
- * before returning.  This is the call bench.py times for the `e2e` figure. */
+/* End-to-end with HOST buffers (pinned recommended; pageable works but its copies are staged and serial): H2D of the
+ * images and prompts, encoder, decoder (one prompt set per image), D2H of masks / iou / optionally embeddings;
+ * synchronises before returning.  Internally the batch is cut into sub-batches of 8 images on two private streams so
+ * the H2D copy of sub-batch i+1 and the D2H copy of sub-batch i-1 overlap the kernels of sub-batch i.
+ * bench.py reports this call as `e2e.c_abi_host` (one synchronous call per step); its headline `e2e` figure is measured
+ * one level up, through the Python Engine API with pinned host tensors, where copies also overlap ACROSS steps. */
 int ullsam_segment_host(ullsam_handle* h, const float* images_host, int B, const float* image_pe_host,
                         const float* sparse_host, int Ns, const float* dense_vec_host, int multimask,
                         float* masks_host, float* iou_host, float* emb_host /* may be NULL */);

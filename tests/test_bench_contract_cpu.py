@@ -22,6 +22,9 @@ def test_reference_arm_prints_the_contract_line():
     assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert "workload" in d["config"] and "model" not in d["config"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config("vit_b", 32, 1, "box")   # identical to the CUDA arm's config object
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]

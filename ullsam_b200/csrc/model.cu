@@ -128,6 +128,8 @@ struct ullsam_handle {
   // host-call staging
   float *d_images = nullptr, *d_pe = nullptr, *d_sparse = nullptr, *d_dense = nullptr, *d_masks = nullptr, *d_iou = nullptr;
   int host_cap_b = 0, host_cap_ns = 0;
+  cudaStream_t hs_copy = nullptr, hs_comp = nullptr;   // internal streams of ullsam_segment_host
+  std::vector<cudaEvent_t> hs_ev;
 };
 
 namespace ullsam {
@@ -828,6 +830,9 @@ void ullsam_destroy(ullsam_handle* h) {
   for (void* p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->weights_ev) cudaEventDestroy(h->weights_ev);
+  for (cudaEvent_t e : h->hs_ev) cudaEventDestroy(e);
+  if (h->hs_copy) cudaStreamDestroy(h->hs_copy);
+  if (h->hs_comp) cudaStreamDestroy(h->hs_comp);
   if (h->staging) cudaFree(h->staging);
   if (h->staging_raw) cudaFree(h->staging_raw);
   delete h;
@@ -1043,9 +1048,8 @@ int ullsam_segment_host(ullsam_handle* h, const float* images_host, int B, const
   if (int rc = check_ready(h, 1)) return rc;
   if (int rc = check_ready(h, 2)) return rc;
   DEVICE_GUARD(h);
-  if (int rc = weights_fence(h, 0)) return rc;
   const int cnt = multimask ? 3 : 1;
-  const size_t img = static_cast<size_t>(3) * 1024 * 1024;
+  const size_t img = static_cast<size_t>(3) * 1024 * 1024, embn = static_cast<size_t>(256) * 4096;
   if (B > h->host_cap_b || Ns > h->host_cap_ns) {
     for (void* p : {(void*)h->d_images, (void*)h->d_pe, (void*)h->d_sparse, (void*)h->d_dense, (void*)h->d_masks, (void*)h->d_iou})
       dfree(h, p);
@@ -1064,25 +1068,59 @@ int ullsam_segment_host(ullsam_handle* h, const float* images_host, int B, const
     h->host_cap_ns = cn;
   }
   if (int rc = ensure_encoder_ws(h, B < kEncChunk ? B : kEncChunk)) return rc;
-  cudaStream_t st = 0;
-  CKC(cudaMemcpyAsync(h->d_images, images_host, B * img * 4, cudaMemcpyHostToDevice, st));
-  CKC(cudaMemcpyAsync(h->d_pe, image_pe_host, 256 * 4096 * 4, cudaMemcpyHostToDevice, st));
-  CKC(cudaMemcpyAsync(h->d_sparse, sparse_host, static_cast<size_t>(B) * Ns * 256 * 4, cudaMemcpyHostToDevice, st));
-  CKC(cudaMemcpyAsync(h->d_dense, dense_vec_host, 256 * 4, cudaMemcpyHostToDevice, st));
-  for (int b0 = 0; b0 < B; b0 += kEncChunk) {
-    const int Bc = (B - b0 < kEncChunk) ? (B - b0) : kEncChunk;
-    if (int rc = encoder_chunk(h, h->d_images + b0 * img, ULLSAM_F32, Bc, h->emb_f32, st)) return rc;
-    if (emb_host)
-      CKC(cudaMemcpyAsync(emb_host + static_cast<size_t>(b0) * 256 * 4096, h->emb_f32, static_cast<size_t>(Bc) * 256 * 4096 * 4,
-                          cudaMemcpyDeviceToHost, st));
-    if (int rc = decoder_run(h, h->emb_f32, Bc, h->d_pe, h->d_sparse + static_cast<size_t>(b0) * Ns * 256, 1, Ns, h->d_dense, 1, 1,
-                             multimask ? 1 : 0, cnt, h->d_masks + static_cast<size_t>(b0) * cnt * 65536,
-                             h->d_iou + static_cast<size_t>(b0) * cnt, st))
-      return rc;
+  // Two internal streams: the copy stream moves sub-batch i+1 of the images to the device (and results back) while the
+  // compute stream runs encoder + decoder on sub-batch i, so only the first sub-batch's H2D and the last one's D2H are
+  // exposed (pinned host buffers; pageable memory degrades to staged, serial copies).
+  constexpr int kSub = 8, kMaxSub = kEncChunk / kSub;
+  if (!h->hs_copy) {
+    CKC(cudaStreamCreateWithFlags(&h->hs_copy, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&h->hs_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2 * kMaxSub; ++i) {
+      cudaEvent_t e;
+      CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->hs_ev.push_back(e);
+    }
   }
-  CKC(cudaMemcpyAsync(masks_host, h->d_masks, static_cast<size_t>(B) * cnt * 65536 * 4, cudaMemcpyDeviceToHost, st));
-  CKC(cudaMemcpyAsync(iou_host, h->d_iou, static_cast<size_t>(B) * cnt * 4, cudaMemcpyDeviceToHost, st));
-  CKC(cudaStreamSynchronize(st));
+  cudaStream_t cs = h->hs_copy, ks = h->hs_comp;
+  if (int rc = weights_fence(h, ks)) return rc;
+  CKC(cudaMemcpyAsync(h->d_pe, image_pe_host, 256 * 4096 * 4, cudaMemcpyHostToDevice, cs));
+  CKC(cudaMemcpyAsync(h->d_sparse, sparse_host, static_cast<size_t>(B) * Ns * 256 * 4, cudaMemcpyHostToDevice, cs));
+  CKC(cudaMemcpyAsync(h->d_dense, dense_vec_host, 256 * 4, cudaMemcpyHostToDevice, cs));
+  for (int c0 = 0; c0 < B; c0 += kEncChunk) {          // outer chunk: what the embedding staging buffer holds
+    const int Bo = (B - c0 < kEncChunk) ? (B - c0) : kEncChunk;
+    const int nsub = (Bo + kSub - 1) / kSub;
+    for (int i = 0; i < nsub; ++i) {
+      const int b0 = c0 + i * kSub, Bc = (Bo - i * kSub < kSub) ? (Bo - i * kSub) : kSub;
+      CKC(cudaMemcpyAsync(h->d_images + b0 * img, images_host + b0 * img, Bc * img * 4, cudaMemcpyHostToDevice, cs));
+      CKC(cudaEventRecord(h->hs_ev[i], cs));
+    }
+    for (int i = 0; i < nsub; ++i) {
+      const int b0 = c0 + i * kSub, Bc = (Bo - i * kSub < kSub) ? (Bo - i * kSub) : kSub;
+      float* emb = h->emb_f32 + static_cast<size_t>(i * kSub) * embn;
+      CKC(cudaStreamWaitEvent(ks, h->hs_ev[i], 0));
+      if (int rc = encoder_chunk(h, h->d_images + b0 * img, ULLSAM_F32, Bc, emb, ks)) return rc;
+      if (int rc = decoder_run(h, emb, Bc, h->d_pe, h->d_sparse + static_cast<size_t>(b0) * Ns * 256, 1, Ns, h->d_dense, 1, 1,
+                               multimask ? 1 : 0, cnt, h->d_masks + static_cast<size_t>(b0) * cnt * 65536,
+                               h->d_iou + static_cast<size_t>(b0) * cnt, ks))
+        return rc;
+      CKC(cudaEventRecord(h->hs_ev[kMaxSub + i], ks));
+    }
+    for (int i = 0; i < nsub; ++i) {
+      const int b0 = c0 + i * kSub, Bc = (Bo - i * kSub < kSub) ? (Bo - i * kSub) : kSub;
+      CKC(cudaStreamWaitEvent(cs, h->hs_ev[kMaxSub + i], 0));
+      CKC(cudaMemcpyAsync(masks_host + static_cast<size_t>(b0) * cnt * 65536, h->d_masks + static_cast<size_t>(b0) * cnt * 65536,
+                          static_cast<size_t>(Bc) * cnt * 65536 * 4, cudaMemcpyDeviceToHost, cs));
+      CKC(cudaMemcpyAsync(iou_host + static_cast<size_t>(b0) * cnt, h->d_iou + static_cast<size_t>(b0) * cnt,
+                          static_cast<size_t>(Bc) * cnt * 4, cudaMemcpyDeviceToHost, cs));
+      if (emb_host)
+        CKC(cudaMemcpyAsync(emb_host + static_cast<size_t>(b0) * embn, h->emb_f32 + static_cast<size_t>(i * kSub) * embn,
+                            static_cast<size_t>(Bc) * embn * 4, cudaMemcpyDeviceToHost, cs));
+    }
+    // (the next outer chunk's H2D copies queue behind these D2H copies on the copy stream, and its compute waits for
+    //  them through hs_ev[i], so the staging buffers are never overwritten while they are still being read)
+  }
+  CKC(cudaStreamSynchronize(cs));
+  CKC(cudaStreamSynchronize(ks));
   return ULLSAM_OK;
 }
 

@@ -62,6 +62,48 @@ def gather_batch(local: Optional[torch.Tensor], n_items: int, group: Optional[di
     return torch.cat([out[r * mx: r * mx + s] for r, s in enumerate(sizes)], dim=0)
 
 
+class AsyncGather:
+    """The path's only collective — the all-gather of a step's mask logits / IoU scores — issued on a
+    SIDE stream, so that it overlaps the next step's encoder instead of stalling the compute stream on the slowest rank.
+
+        ag = AsyncGather(device)
+        for step in ...:
+            masks, iou = decode(...)                      # on the current (compute) stream
+            ag.submit([masks, iou], [all_masks[step & 1], all_iou[step & 1]])
+        ag.wait()                                         # current stream waits for every gather queued so far
+
+    ``comm_ms()`` returns the device time spent inside the gathers (CUDA events on the side stream) and resets it."""
+
+    def __init__(self, device: torch.device, group: Optional[dist.ProcessGroup] = None, timing: bool = True):
+        self.device, self.group, self.timing = device, group, timing
+        self.stream = torch.cuda.Stream(device)
+        self._spans: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
+
+    def submit(self, shards: Sequence[torch.Tensor], outs: Sequence[torch.Tensor]) -> None:
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            if self.timing:
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(self.stream)
+            for shard, out in zip(shards, outs):
+                dist.all_gather_into_tensor(out, shard, group=self.group)
+                shard.record_stream(self.stream)      # the allocator must not recycle the shard before the gather ran
+            if self.timing:
+                t1.record(self.stream)
+                self._spans.append((t0, t1))
+
+    def wait(self) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def comm_ms(self) -> float:
+        self.stream.synchronize()
+        total = sum(a.elapsed_time(b) for a, b in self._spans)
+        self._spans.clear()
+        return total
+
+
 def segment_sharded(engine, images: torch.Tensor, image_pe: torch.Tensor, sparse: torch.Tensor, dense: torch.Tensor,
                     multimask_output: bool, group: Optional[dist.ProcessGroup] = None, gather_embeddings: bool = False):
     """Every rank passes the SAME global batch description (``images`` may be any tensor whose dim 0 is the global
