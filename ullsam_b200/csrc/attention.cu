@@ -42,6 +42,9 @@
 #else
 #define TL_STAMP(i) do { } while (0)
 #endif
+#ifndef ULLSAM_ATT_SOLO
+#define ULLSAM_ATT_SOLO 0
+#endif
 #ifndef ULLSAM_ATT_GLOBAL_ONE_THREAD
 #define ULLSAM_ATT_GLOBAL_ONE_THREAD 1
 #endif
@@ -100,6 +103,12 @@ struct AttCfg {
 ULLSAM_DEVICE void tmem_ld_n(uint32_t a, uint32_t (&v)[16]) { tmem_ld16(a, v); }
 ULLSAM_DEVICE void tmem_st_n(uint32_t a, const uint32_t (&v)[8]) { tmem_st8(a, v); }
 
+ULLSAM_DEVICE unsigned tl_smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+
 ULLSAM_DEVICE float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -142,6 +151,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   using A = AttCfg<GRID>;
   constexpr int KS = A::KSTAGES, VS = A::VSTAGES, BN = A::BN, NT = A::NT, QT = A::QT, NSLOT = A::NSLOT, NITEMS = A::NITEMS;
   constexpr int NROWS = A::NROWS;
+#if ULLSAM_ATT_TIMELINE
+  const long long tl_entry = clock64();
+  const bool tl_cta = (blockIdx.x == 0 && blockIdx.y == 0) || (blockIdx.x == 5 && blockIdx.y == gridDim.y / 2);
+#endif
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms, computed as an offset so the pointer stays in the shared window
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -463,6 +476,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       long long tl[7] = {0, 0, 0, 0, 0, 0, 0};
       long long tl_last = clock64();
       const long long tl_begin = tl_last;
+      int tl_wait[NT], tl_at[NT];
 #endif
 #pragma unroll 1
       for (int j = 0; j < NT; ++j) {
@@ -471,7 +485,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         TL_STAMP(5);
         mbar_wait(&s_full[n % NSLOT], (n / NSLOT) & 1);
         tc_fence_after();
+#if ULLSAM_ATT_TIMELINE
+        tl_wait[j] = static_cast<int>(clock64() - tl_last);
+        tl_at[j] = static_cast<int>(clock64() - tl_begin);
+#endif
         TL_STAMP(0);
+#if ULLSAM_ATT_SOLO   // timing experiment only (wrong results): query tile 1 does no softmax work, so tile 0's warps have the MUFU alone
+        if (qt == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_ready[qt]);
+          mbar_wait(&o_done[qt * 2 + (j & 1)], (j >> 1) & 1);   // keep pace with the MMA warp (it must observe every p_ready phase)
+          continue;
+        }
+#endif
 
         constexpr int PIECE = ULLSAM_ATT_PIECE, NP = 128 / PIECE;
         uint32_t pb[2][PIECE];
@@ -590,9 +617,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #endif
       }
 #if ULLSAM_ATT_TIMELINE
-      if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && quad == 0)
+      if (tl_cta && lane == 0 && quad == 0)
         printf("qt %d: per tile: wait S %lld | pass A %lld | rescale %lld | pass B %lld | tail %lld | loop %lld | PV probe %lld | total/tile %lld\n",
                qt, tl[0] / NT, tl[1] / NT, tl[2] / NT, tl[3] / NT, tl[4] / NT, tl[5] / NT, tl[6] / NT, (clock64() - tl_begin) / NT);
+      if (tl_cta && lane == 0 && quad == 0 && blockIdx.y != 0)
+        for (int j = 0; j < NT; ++j) printf("  qt %d tile %2d: S seen at %6d after waiting %5d\n", qt, j, tl_at[j], tl_wait[j]);
 #endif
 
       // ---- epilogue: O / l -> out ----
@@ -614,6 +643,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                                       pack_bf16(__uint_as_float(o[8 * u + 4]) * inv_l, __uint_as_float(o[8 * u + 5]) * inv_l),
                                       pack_bf16(__uint_as_float(o[8 * u + 6]) * inv_l, __uint_as_float(o[8 * u + 7]) * inv_l));
       }
+#if ULLSAM_ATT_TIMELINE
+      if (tl_cta && lane == 0 && quad == 0)
+        printf("cta (%d,%d) qt %d: entry -> loop begin %lld | loop %lld | loop end -> stored %lld | smid %d\n", blockIdx.x, blockIdx.y, qt,
+               tl_begin - tl_entry, tl_last - tl_begin, clock64() - tl_last, (int)tl_smid());
+#endif
     }
   } else if (A::SPLIT == 2) {
     // =========================================== softmax warps, two threads per query row ================
