@@ -1,0 +1,11 @@
+#!/bin/bash
+# Round-2 call 13: two MMA-issuing warps in the global attention: parity, determinism, A/B timing, schedule trace.
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_ops_attention_gpu.py -x -q -m gpu -s 2>&1 | grep -E "global|determin|passed|failed|Error|error|timeout" | head -20
+bash tools/ab_variants.sh nola default t2nola t1la
+for v in timeline; do
+  echo "=== $v"
+  ULLSAM_B200_LIB=variants/lib_$v.so timeout 120 python tools/time_attention_once.py 1 > gpurun_out/r2_sched_$v.log 2>&1
+  grep "^  at" gpurun_out/r2_sched_$v.log | sort -k2 -n | head -40
+  grep "per tile\|mma warp\|cta (5" gpurun_out/r2_sched_$v.log
+done

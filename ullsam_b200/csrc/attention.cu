@@ -103,11 +103,13 @@ struct AttCfg {
 ULLSAM_DEVICE void tmem_ld_n(uint32_t a, uint32_t (&v)[16]) { tmem_ld16(a, v); }
 ULLSAM_DEVICE void tmem_st_n(uint32_t a, const uint32_t (&v)[8]) { tmem_st8(a, v); }
 
+#if ULLSAM_ATT_TIMELINE
 ULLSAM_DEVICE unsigned tl_smid() {
   unsigned r;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
   return r;
 }
+#endif
 
 ULLSAM_DEVICE float ex2(float x) {
   float y;
@@ -330,6 +332,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #if ULLSAM_ATT_TIMELINE
       long long mma_tl[3] = {0, 0, 0};
       long long mma_last = clock64();
+      int mma_p[NITEMS], mma_e[NITEMS];
 #endif
       for (int n = 0; n < NITEMS; ++n) {
         const int j = n / QT, qt = n % QT, vstage = j % VS;
@@ -371,9 +374,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mma_tl[1] += mt1 - mt0;           // waiting for P(n)
         mma_last = clock64();
         mma_tl[2] += mma_last - mt1;      // issuing the MMAs
+        mma_p[n] = static_cast<int>(mt1 - tl_entry);
+        mma_e[n] = static_cast<int>(mma_last - tl_entry);
 #endif
       }
 #if ULLSAM_ATT_TIMELINE
+      if (tl_cta && blockIdx.y != 0 && leader)
+        for (int n = 16; n < 32; ++n) printf("  at %7d item %2d: mma warp saw P, issue done at %7d\n", mma_p[n], n, mma_e[n]);
       if (blockIdx.x == 0 && blockIdx.y == 0 && leader)
         printf("mma warp per item: prep+operand waits %lld | wait P %lld | issue %lld\n", mma_tl[0] / NITEMS, mma_tl[1] / NITEMS,
                mma_tl[2] / NITEMS);
@@ -404,58 +411,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       float* relw_s = reinterpret_cast<float*>(smem + A::OFF_RELW);
       __half* relh_s = reinterpret_cast<__half*>(smem + A::OFF_RELH);
 
-      // ---- prologue: scatter this row's 64 rel_w and 64 rel_h values (log2 units), remember max(rel_w) ----
-      mbar_wait(pro_mma_done, 0);
-      tc_fence_after();
-      float wmax = -INFINITY, hmax_all = -INFINITY;
-#pragma unroll
-      for (int tbl = 0; tbl < 2; ++tbl) {
-        const uint32_t col_t = (tbl ? 256 : 0) + qt * 128;
-        const int q0 = tbl ? qh : qw;
-#pragma unroll
-        for (int c = 0; c < A::NREL / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(lane_addr + col_t + c * 32, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int kk = q0 + (GRID - 1) - (c * 32 + i);
-            if (kk >= 0 && kk < GRID) {
-              const float val = __uint_as_float(v[i]) * kLog2e;
-              if (tbl) {
-                relh_s[kk * NROWS + tidq] = __float2half_rn(val);
-                hmax_all = fmaxf(hmax_all, val);
-              } else {
-                relw_s[((kk >> 2) * NROWS + tidq) * 4 + (kk & 3)] = val;
-                wmax = fmaxf(wmax, val);
-              }
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pro_consumed);  // the prologue's TMEM columns may now be overwritten
-      // the row's 64 rel_w values stay in registers for the whole kernel (they only depend on (q, kw))
-      float wreg[64];
-#pragma unroll
-      for (int k4 = 0; k4 < 16; ++k4) {
-        const float4 w = *reinterpret_cast<const float4*>(relw_s + (k4 * NROWS + tidq) * 4);
-        wreg[4 * k4] = w.x; wreg[4 * k4 + 1] = w.y; wreg[4 * k4 + 2] = w.z; wreg[4 * k4 + 3] = w.w;
-      }
-
-      // ---- main loop ----
-      const float cs = 0.125f * kLog2e;  // head_dim 64: scale = 1/8, folded with log2(e)
-      float m_used = -INFINITY;          // reference point of the exponentials (log2 units)
-      float l0 = 0.f, l1 = 0.f;          // row sum (two accumulation chains)
-      const uint32_t o_addr = lane_addr + A::COL_O + qt * 64;
-      // A-priori bound of EVERY biased score of the row (Cauchy-Schwarz): |q| * max_k |k| * scale + max rel_w + max rel_h,
-      // with max_k |k| of this (image, head) from a tiny pre-pass over K (kmax_norm, may be null).  Once the reference
-      // point chosen on the first tile is within 2^100 of that bound nothing can overflow any more (P is bf16 with an
-      // 8-bit exponent, O and the row sum are fp32), so the maximum pass and the rescale check are skipped for the
-      // remaining 31 tiles; otherwise (huge norms) the kernel keeps checking tile by tile as before.
-      float bound_rest = INFINITY;
+      // ---- prologue: this row's 64 rel_h values -> shared memory, its 64 rel_w values -> registers (log2 units) ----
+      // Row (qh, qw) needs T[row][q0 + 63 - k] for k = 0..63 (q0 = qh resp. qw): a 64-wide window of its 127-entry table row,
+      // reversed.  rel_h: qh is warp-uniform (a warp's 32 rows lie in one image row), so the window is read straight from
+      // tensor memory at a warp-uniform column offset and stored unconditionally.  rel_w: the window start differs lane by
+      // lane, which registers cannot index — each thread parks its table row in a thread-private shared scratch
+      // ([word][thread]: conflict-free for any per-lane word index), 64 columns at a time, and reads it back at its own
+      // offset.  No predicated scatter, no divergence (the first version spent 8.5 K of the CTA's ~98 K cycles here).
+#if ULLSAM_ATT_TIMELINE
+      const long long tp0 = clock64();
+#endif
+      // |q| for the a-priori score bound (below), computed while the table MMAs run; the key-norm load is issued first
+      float qnorm_k = INFINITY;
       if (kmax_norm != nullptr) {
+        const float kmaxv = __ldg(kmax_norm + gh);
+        mbar_wait(q_full, 0);
         const uint8_t* qrow = smem + A::OFF_Q + qt * A::QBYTES + r * 128;   // 128-byte swizzle: 16-byte chunk c at c ^ (r & 7)
         float qq = 0.f;
 #pragma unroll
@@ -468,16 +438,84 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             qq = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, qq));
           }
         }
-        bound_rest = fmaf(sqrtf(qq) * __ldg(kmax_norm + gh), cs, wmax + hmax_all) + 0.0625f;   // (+ slack for the half-rounded rel_h)
+        qnorm_k = sqrtf(qq) * kmaxv;
       }
+      mbar_wait(pro_mma_done, 0);
+      tc_fence_after();
+#if ULLSAM_ATT_TIMELINE
+      const long long tp1 = clock64();
+#endif
+      float wmax = -INFINITY, hmax_all = -INFINITY;
+      {
+        const int qh_u = __shfl_sync(0xffffffffu, qh, 0);            // warp-uniform by construction
+        const uint32_t col_h = lane_addr + 256 + qt * 128 + qh_u;    // Th[row][qh + i] = rel_h[row][kh = 63 - i]
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(col_h + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float val = __uint_as_float(v[i]) * kLog2e;
+            relh_s[(63 - (c * 32 + i)) * NROWS + tidq] = __float2half_rn(val);
+            hmax_all = fmaxf(hmax_all, val);
+          }
+        }
+      }
+      float wreg[64];   // the row's 64 rel_w values stay in registers for the whole kernel (they only depend on (q, kw))
+      {
+        float* scratch = relw_s + tidq;                              // word w of this thread at scratch[w * NROWS]
+        const uint32_t col_w = lane_addr + qt * 128;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                                // table columns [64h, 64h + 64)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(col_w + h * 64 + c * 32, v);
+            tmem_wait_ld();
+            if (h == 1 && c == 1) {                                  // last read of the prologue's tensor-memory columns
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(pro_consumed);              // they may now be overwritten: QK(0..2) start
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) scratch[(c * 32 + i) * NROWS] = __uint_as_float(v[i]) * kLog2e;
+          }
+#pragma unroll
+          for (int kw = 0; kw < 64; ++kw) {
+            const int rho = qw + 63 - kw;                            // table column of key-grid column kw
+            const float t = scratch[(rho & 63) * NROWS];
+            wreg[kw] = (h == 0 || rho >= 64) ? t : wreg[kw];         // h = 0 fills everything, h = 1 corrects kw < qw
+          }
+        }
+#pragma unroll
+        for (int kw = 0; kw < 64; kw += 2) wmax = fmax3(wmax, wreg[kw], wreg[kw + 1]);
+      }
+#if ULLSAM_ATT_TIMELINE
+      const long long tp2 = clock64();
+#endif
+
+      // ---- main loop ----
+      const float cs = 0.125f * kLog2e;  // head_dim 64: scale = 1/8, folded with log2(e)
+      float m_used = -INFINITY;          // reference point of the exponentials (log2 units)
+      float l0 = 0.f, l1 = 0.f;          // row sum (two accumulation chains)
+      const uint32_t o_addr = lane_addr + A::COL_O + qt * 64;
+      // A-priori bound of EVERY biased score of the row (Cauchy-Schwarz): |q| * max_k |k| * scale + max rel_w + max rel_h,
+      // with max_k |k| of this (image, head) from a tiny pre-pass over K (kmax_norm, may be null).  Once the reference
+      // point chosen on the first tile is within 2^100 of that bound nothing can overflow any more (P is bf16 with an
+      // 8-bit exponent, O and the row sum are fp32), so the maximum pass and the rescale check are skipped for the
+      // remaining 31 tiles; otherwise (huge norms) the kernel keeps checking tile by tile as before.
+      const float bound_rest = kmax_norm != nullptr ? fmaf(qnorm_k, cs, wmax + hmax_all) + 0.0625f   // (+ slack for the half-rounded rel_h)
+                                                    : INFINITY;
       bool skip_max = false;
 
 #if ULLSAM_ATT_TIMELINE
       long long tl[7] = {0, 0, 0, 0, 0, 0, 0};
       long long tl_last = clock64();
       const long long tl_begin = tl_last;
-      int tl_wait[NT], tl_at[NT];
+      int tl_wait[NT], tl_at[NT], tl_pr[NT];
 #endif
+      constexpr int PIECE = ULLSAM_ATT_PIECE, NP = 128 / PIECE;
 #pragma unroll 1
       for (int j = 0; j < NT; ++j) {
         const int n = j * QT + qt;
@@ -485,9 +523,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         TL_STAMP(5);
         mbar_wait(&s_full[n % NSLOT], (n / NSLOT) & 1);
         tc_fence_after();
+        uint32_t pb[2][PIECE];
+        const float rh0 = __half2float(relh_s[(2 * j) * NROWS + tidq]);
+        const float rh1 = __half2float(relh_s[(2 * j + 1) * NROWS + tidq]);
 #if ULLSAM_ATT_TIMELINE
         tl_wait[j] = static_cast<int>(clock64() - tl_last);
-        tl_at[j] = static_cast<int>(clock64() - tl_begin);
+        tl_at[j] = static_cast<int>(clock64() - tl_entry);
 #endif
         TL_STAMP(0);
 #if ULLSAM_ATT_SOLO   // timing experiment only (wrong results): query tile 1 does no softmax work, so tile 0's warps have the MUFU alone
@@ -500,10 +541,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
 #endif
 
-        constexpr int PIECE = ULLSAM_ATT_PIECE, NP = 128 / PIECE;
-        uint32_t pb[2][PIECE];
-        const float rh0 = __half2float(relh_s[(2 * j) * NROWS + tidq]);
-        const float rh1 = __half2float(relh_s[(2 * j + 1) * NROWS + tidq]);
         if (skip_max) {
           tmem_ld_n(s_addr, pb[0]);   // first piece of pass B
         } else {
@@ -607,6 +644,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[qt]);
+#if ULLSAM_ATT_TIMELINE
+        tl_pr[j] = static_cast<int>(clock64() - tl_entry);
+#endif
         TL_STAMP(4);
 #if ULLSAM_ATT_TIMELINE == 2
         mbar_wait(&o_done[qt * 2 + (j & 1)], (j >> 1) & 1);  // probe: P(n) handed over -> PV(n) retired
@@ -621,7 +661,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         printf("qt %d: per tile: wait S %lld | pass A %lld | rescale %lld | pass B %lld | tail %lld | loop %lld | PV probe %lld | total/tile %lld\n",
                qt, tl[0] / NT, tl[1] / NT, tl[2] / NT, tl[3] / NT, tl[4] / NT, tl[5] / NT, tl[6] / NT, (clock64() - tl_begin) / NT);
       if (tl_cta && lane == 0 && quad == 0 && blockIdx.y != 0)
-        for (int j = 0; j < NT; ++j) printf("  qt %d tile %2d: S seen at %6d after waiting %5d\n", qt, j, tl_at[j], tl_wait[j]);
+        for (int j = 8; j < 16; ++j)
+          printf("  at %7d item %2d: qt %d tile %2d starts (waited %4d), P handed over at %7d\n", tl_at[j], 2 * j + qt, qt, j,
+                 tl_wait[j], tl_pr[j]);
 #endif
 
       // ---- epilogue: O / l -> out ----
@@ -644,6 +686,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                                       pack_bf16(__uint_as_float(o[8 * u + 6]) * inv_l, __uint_as_float(o[8 * u + 7]) * inv_l));
       }
 #if ULLSAM_ATT_TIMELINE
+      if (tl_cta && lane == 0 && quad == 0)
+        printf("cta (%d,%d) qt %d: entry -> role start %lld | -> tables computed %lld | -> scattered %lld | -> loop begin %lld\n", blockIdx.x, blockIdx.y, qt,
+               tp0 - tl_entry, tp1 - tp0, tp2 - tp1, tl_begin - tp2);
       if (tl_cta && lane == 0 && quad == 0)
         printf("cta (%d,%d) qt %d: entry -> loop begin %lld | loop %lld | loop end -> stored %lld | smid %d\n", blockIdx.x, blockIdx.y, qt,
                tl_begin - tl_entry, tl_last - tl_begin, clock64() - tl_last, (int)tl_smid());

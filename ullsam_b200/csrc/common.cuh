@@ -97,6 +97,21 @@ ULLSAM_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// Non-blocking probe (mbarrier.test_wait never suspends the thread): has the phase with this parity completed?
+ULLSAM_DEVICE bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) after ~4 s of wall time instead of a hung
 // GPU.  The clock is only read once the wait has already failed 256 times, so the normal path costs nothing.
 ULLSAM_DEVICE uint64_t global_timer_ns() {
