@@ -177,7 +177,11 @@ typedef struct {
   float ln_eps;
   int32_t hw;
   void* out2;           /* epi 11: bf16 LayerNorm(out) [M, N] (token order) or [M/4096*25*196, N] (window order) */
-  int32_t ln_partition; /* epi 11: 1 = window order (pad rows are not written) */
+  int32_t ln_partition; /* epi 11: 1 = window order (pad rows are not written)
+                         * epi 2: 1 = A's rows are the image tokens [B,64,64]; the store performs window_partition
+                         *        (image_encoder.py:243-264) into q/k/v [B*25][heads][196][64] and also writes the k / v rows
+                         *        of the 804 padding tokens per image (= bias: they are zero after norm1, :168-172, and
+                         *        are attended to); their q rows are left untouched (cropped by window_unpartition) */
 } ullsam_gemm_desc;
 int ullsam_op_gemm(const ullsam_gemm_desc* d, void* stream);
 

@@ -111,6 +111,31 @@ def test_gemm_qkv_split(T, G):
         _close(got, r, 8e-3, f"qkv[{name}] T={T}")
 
 
+def test_gemm_qkv_window_partition_on_store():
+    """The windowed blocks' QKV projection (image_encoder.py:168-172, 227-229): the reference zero-pads the normalised
+    64x64 map to 70x70, partitions it into 25 windows of 14x14 and projects all 4900 tokens per image.  Here the GEMM runs
+    on the 4096 image tokens; its epilogue scatters the rows into the windows and writes k = v = bias for the 804 padding
+    tokens (q rows of padding tokens are never used: window_unpartition crops them)."""
+    from ullsam_b200 import _lib, ops
+
+    B, heads, dim = 2, 12, 768
+    a, w, b = _mk(B * 4096, 3 * dim, dim, 5)
+    q = torch.full((B * 25, heads, 196, 64), 7.0, dtype=torch.bfloat16, device="cuda")
+    k, v = q.clone(), q.clone()
+    ops.gemm(a, w, b, epi=_lib.EPI_QKV, qkv=(q, k, v), T=196, heads=heads, ln_partition=True)
+    # reference: pad the INPUT with zero rows, partition, project (bias included)
+    x = a.float().reshape(B, 64, 64, dim)
+    xp = torch.nn.functional.pad(x, (0, 0, 0, 6, 0, 6))
+    win = xp.reshape(B, 5, 14, 5, 14, dim).permute(0, 1, 3, 2, 4, 5).reshape(B * 25 * 196, dim)
+    ref = (win @ w.float().t() + b).reshape(B * 25, 196, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    valid = torch.nn.functional.pad(torch.ones(B, 64, 64, device="cuda"), (0, 6, 0, 6))
+    valid = valid.reshape(B, 5, 14, 5, 14).permute(0, 1, 3, 2, 4).reshape(B * 25, 1, 196, 1).bool()
+    for name, got, r in (("k", k, ref[1]), ("v", v, ref[2])):
+        _close(got, r, 8e-3, f"windowed qkv[{name}]")
+    _close(torch.where(valid, q.float(), ref[0]), ref[0], 8e-3, "windowed qkv[q] (real tokens)")
+    assert (q.float()[(~valid).expand_as(q)] == 7.0).all(), "q rows of padding tokens must stay untouched"
+
+
 def _ln2d(x, w, b, eps):
     u = x.mean(-1, keepdim=True)
     s = (x - u).pow(2).mean(-1, keepdim=True)

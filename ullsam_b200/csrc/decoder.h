@@ -22,6 +22,33 @@ struct TokLinear {
   int act;  // 0 none, 2 ReLU
 };
 
+// ---- fused token side (decoder_fused.cu): one cluster-of-four kernel per TwoWayAttentionBlock -------------------------------
+constexpr int kDecFusedMaxTokens = 24;   // prompt tokens per prompt (1 + 4 + Ns) the fused kernels hold in shared memory
+struct DecTokLayer {   // token-side weights of one block, fp32, nn.Linear layout [out][in]  (transformer.py:125-151)
+  const float *sq_w, *sq_b, *sk_w, *sk_b, *sv_w, *sv_b, *so_w, *so_b;   // self_attn q/k/v/out_proj, 256 x 256
+  const float *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b;
+  const float *tq_w, *tq_b, *to_w, *to_b;     // cross_attn_token_to_image q_proj [128][256], out_proj [256][128]
+  const float *m1_w, *m1_b, *m2_w, *m2_b;     // mlp lin1 [2048][256], lin2 [256][2048]
+  const float *ik_w, *ik_b, *iv_w, *iv_b;     // cross_attn_image_to_token k_proj / v_proj [128][256]
+  int mlp_dim;
+  int skip_pe;                                // first block: skip_first_layer_pe (transformer.py:157-158)
+};
+struct DecTokFinal {   // final_attn_token_to_image + norm_final_attn (transformer.py:98-106), hypernets + IoU head (mask_decoder.py:59-69)
+  const float *tq_w, *tq_b, *to_w, *to_b, *nf_w, *nf_b;
+  const float *hyp_w0, *hyp_b0, *hyp_w1, *hyp_b1, *hyp_w2, *hyp_b2;   // [4][256][256], [4][256], [4][256][256], [4][256], [4][32][256], [4][32]
+  const float* iou_w[4];
+  const float* iou_b[4];
+  int iou_depth, iou_hidden;
+};
+bool dec_tokens_fused_supported(int Nt, int mlp_dim, int iou_hidden);
+// queries fp32 [R][Nt][256] in/out; tokens = point embedding [R][Nt][256]; proj bf16 [R*4096][ldkv] (K cols 0..127, V 128..255);
+// k128 / v128 fp32 [R][Nt][128] out (the tokens' keys / values for the image->token attention)
+const char* launch_dec_token_layer(const DecTokLayer& L, float* queries, const float* tokens, const __nv_bfloat16* proj, int ldkv,
+                                   int R, int Nt, float* k128, float* v128, cudaStream_t stream);
+// hyper fp32 [R][4][32] and iou4 fp32 [R][4] may be nullptr (TwoWayTransformer alone)
+const char* launch_dec_token_final(const DecTokFinal& F, float* queries, const float* tokens, const __nv_bfloat16* proj, int ldkv,
+                                   int R, int Nt, float* hyper, float* iou4, cudaStream_t stream);
+
 const char* launch_tok_linear(const TokLinear& a, cudaStream_t stream);
 const char* launch_tok_self_attn(const float* q, const float* k, const float* v, int R, int Nt, float* out,
                                  cudaStream_t stream);

@@ -121,6 +121,8 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
     if (!p.out2 || !p.ln_w || !p.ln_b || !p.residual) return "gemm: EPI_RES_LN needs residual, ln_w, ln_b and out2";
     if (p.ln_partition && p.M % 4096 != 0) return "gemm: EPI_RES_LN window partition needs whole 64x64 token grids";
   }
+  if (epi == EPI_QKV && p.ln_partition && (p.M % 4096 != 0 || p.T != 196))
+    return "gemm: EPI_QKV window scatter needs whole 64x64 token grids and T == 196";
   const bool pair = (epi == EPI_RES_LN) ||
                     (!pair_disabled && bn == 256 && !p.a_conv3 && p.M >= 4096 &&
                      (epi == EPI_BF16 || epi == EPI_GELU_BF16 || epi == EPI_RES_F32 || epi == EPI_QKV));

@@ -56,6 +56,9 @@ struct GemmParams {
   void* out2;          // EPI_LN_RES / EPI_RES_LN: bf16 copy of the normalised rows
   int ln_partition;    // EPI_RES_LN: 0 = out2 rows in token order, 1 = 14x14-window-partitioned order (25 windows of 196
                        // rows per image; the zero pad rows are never written here)
+                       // EPI_QKV: 1 = the rows of A are the image tokens [B,64,64]; the epilogue scatters them into the
+                       // 14x14 windows of q/k/v [B*25][heads][196][64] (T must be 196) and writes k = v = bias for the
+                       // padding tokens (their q rows are not written)
   const float* hyper;  // EPI_MASK: hyper_in [R][4][32]
   int mask_m0;         // EPI_MASK: first mask channel written
   int mask_cnt;        // EPI_MASK: number of mask channels written (out is [R][mask_cnt][256][256] fp32)

@@ -596,8 +596,60 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int grow = tile_row0 + it * 8 + rr;
-            const int g = grow / p.T, t = grow - g * p.T;
+            int g, t;
+            if (p.ln_partition) {
+              // rows are image tokens (b, y, x) of the 64 x 64 grid: window_partition (image_encoder.py:243-264) happens
+              // here, on the store — the GEMM never sees the 804 padding tokens per image (their k / v rows are the bias,
+              // written by kv_pad_fill_kernel)
+              const int b = grow >> 12, y = (grow >> 6) & 63, x = grow & 63;
+              const int wy = y / 14, wx = x / 14;
+              g = (b * 5 + wy) * 5 + wx;
+              t = (y - wy * 14) * 14 + (x - wx * 14);
+            } else {
+              g = grow / p.T;
+              t = grow - g * p.T;
+            }
             qkv_row_off[it] = (static_cast<size_t>(g) * p.heads * p.T + t) * 64;
+          }
+          // The k / v rows of the window-PADDING tokens (804 per image: the normalised map is zero-padded to 70 x 70 before the
+          // projection, so they equal the bias and are attended to, image_encoder.py:168-172) ride on this epilogue: every
+          // 32-row unit of the image (128 of them) writes its 1/128 share of the pad tokens for the columns it owns —
+          // six or seven 256-byte rows next to the unit's own 32, no extra kernel and no extra pass over memory.
+          if (p.ln_partition && p.bias != nullptr) {
+            constexpr int CHUNKS = COLS_PER_WARP / 8;              // 16-byte chunks per pad row in this warp's columns
+            constexpr int TOK_PER_INST = 32 / CHUNKS;
+            static_assert(CHUNKS == 8 || CHUNKS == 16, "pad rows: 64 or 128 columns per epilogue warp");
+            const int dim = p.heads * 64;
+            const int unit = (tile_row0 & 4095) >> 5, img = tile_row0 >> 12;
+            const int id0 = unit * 804 / 128, id1 = (unit + 1) * 804 / 128;
+            const int chunk = lane % CHUNKS;
+            const int ncol = col0 + chunk * 8;
+            const int which = ncol / dim, rem = ncol - which * dim;
+            if (which != 0 && tile_row0 < p.M) {
+#if ULLSAM_GEMM_BIAS_SMEM
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + chunk * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + chunk * 8 + 4);
+#else
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol + 4));
+#endif
+              const uint4 val = make_uint4(pack_bf16(b0.x, b0.y), pack_bf16(b0.z, b0.w), pack_bf16(b1.x, b1.y), pack_bf16(b1.z, b1.w));
+              __nv_bfloat16* base = (which == 1 ? p.k : p.v) + static_cast<size_t>(rem >> 6) * p.T * 64 + (rem & 63);
+              for (int id = id0 + lane / CHUNKS; id < id1; id += TOK_PER_INST) {
+                // pad token id -> (yy, xx) of the 70 x 70 padded map: 6 full bottom rows (420 tokens), then the right strip
+                int yy, xx;
+                if (id < 420) {
+                  yy = 64 + id / 70;
+                  xx = id % 70;
+                } else {
+                  yy = (id - 420) / 6;
+                  xx = 64 + (id - 420) % 6;
+                }
+                const int wy = yy / 14, wx = xx / 14;
+                const int g = (img * 5 + wy) * 5 + wx, t = (yy - wy * 14) * 14 + (xx - wx * 14);
+                *reinterpret_cast<uint4*>(base + (static_cast<size_t>(g) * p.heads * p.T + t) * 64) = val;
+              }
+            }
           }
         }
         // The TMEM load of chunk c+1 is in flight while chunk c is processed (two register buffers, loop fully

@@ -108,7 +108,7 @@ struct ullsam_handle {
   // workspaces
   int enc_cap = 0;
   float* x = nullptr;
-  bf16 *xn = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *ao = nullptr, *hid = nullptr;
+  bf16 *q = nullptr, *k = nullptr, *v = nullptr, *ao = nullptr, *hid = nullptr;
   float* kmax = nullptr;  // [kEncChunk * heads] max key norm per (image, head): scratch of the global attention
   bf16* xn_t = nullptr;  // LayerNorm outputs in token order (xn holds the window-partitioned ones: its pad rows stay zero)
   float* emb_f32 = nullptr;  // [cap,256,4096] when the caller wants bf16 output / host staging
@@ -447,13 +447,12 @@ int check_ready(ullsam_handle* h, int which) {
 
 int ensure_encoder_ws(ullsam_handle* h, int B) {
   if (B <= h->enc_cap) return ULLSAM_OK;
-  for (void* p : {(void*)h->x, (void*)h->xn, (void*)h->xn_t, (void*)h->kmax, (void*)h->q, (void*)h->k, (void*)h->v, (void*)h->ao, (void*)h->hid,
+  for (void* p : {(void*)h->x, (void*)h->xn_t, (void*)h->kmax, (void*)h->q, (void*)h->k, (void*)h->v, (void*)h->ao, (void*)h->hid,
                   (void*)h->emb_f32})
     dfree(h, p);
   const size_t D = h->cfg.embed_dim, M = h->cfg.mlp_dim;
   const size_t tokw = static_cast<size_t>(B) * 4900, tok = static_cast<size_t>(B) * 4096;
   h->x = dalloc<float>(h, tok * D);
-  h->xn = dalloc<bf16>(h, tokw * D);
   h->xn_t = dalloc<bf16>(h, tok * D);
   h->kmax = dalloc<float>(h, static_cast<size_t>(B) * h->cfg.num_heads);
   h->q = dalloc<bf16>(h, tokw * D);
@@ -462,13 +461,13 @@ int ensure_encoder_ws(ullsam_handle* h, int B) {
   h->ao = dalloc<bf16>(h, tok * D);
   h->hid = dalloc<bf16>(h, tok * (M > 768 ? M : 768));
   h->emb_f32 = dalloc<float>(h, tok * 256);
-  if (!h->x || !h->xn || !h->xn_t || !h->kmax || !h->q || !h->k || !h->v || !h->ao || !h->hid || !h->emb_f32) {
+  if (!h->x || !h->xn_t || !h->kmax || !h->q || !h->k || !h->v || !h->ao || !h->hid || !h->emb_f32) {
     h->enc_cap = 0;
     return fail(h, ULLSAM_ERR_NOMEM, "cudaMalloc failed for the encoder workspace");
   }
-  // window_partition's zero pad rows (image_encoder.py:257-259): the fused residual+LayerNorm epilogue only writes the
-  // real rows of this buffer and nothing else ever writes the pad rows, so they are cleared once here
-  if (cudaMemset(h->xn, 0, tokw * D * sizeof(bf16)) != cudaSuccess) {
+  // q rows of the window-padding tokens are never written (their outputs are cropped, image_encoder.py:267-289, and
+  // attention rows are independent): give them defined contents once
+  if (cudaMemset(h->q, 0, tokw * D * sizeof(bf16)) != cudaSuccess) {
     h->enc_cap = 0;
     return fail(h, ULLSAM_ERR_CUDA, "cudaMemset failed for the encoder workspace");
   }
@@ -534,7 +533,7 @@ GemmParams gp(int M, int N, int K) {
 int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float* out_f32, cudaStream_t st) {
   const auto& c = h->cfg;
   const int D = c.embed_dim, MD = c.mlp_dim, heads = c.num_heads, sms = h->sms;
-  const int tok = Bc * 4096, tokw = Bc * 4900;
+  const int tok = Bc * 4096;
   // PatchEmbed (+ pos_embed)
   CKS(launch_im2col16(images, dtype == ULLSAM_BF16, Bc, 3, 1024, h->hid, st));
   {
@@ -556,17 +555,18 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
   for (int i = 0; i < c.depth; ++i) {
     const EncBlock& b = h->blocks[i];
     const int win = b.global ? 0 : c.window_size;
-    const int Mq = b.global ? tok : tokw, T = b.global ? 4096 : 196;
-    bf16* xin = b.global ? h->xn_t : h->xn;   // norm1 output: token order / window-partitioned order
+    const int T = b.global ? 4096 : 196;
+    // norm1 output stays in token order for windowed blocks too: window_partition (image_encoder.py:168-172, 243-264) is
+    // done by the QKV epilogue on the store, so the GEMM runs on the 4096 image tokens instead of the 4900 padded ones
+    // (-16 % of its rows); the constant k / v rows of the 804 padding tokens (= qkv.bias) ride on the same epilogue.
     if (i == 0 || !fuse_ln1) {
-      // norm1 (+ window_partition)
-      CKS(launch_layernorm(h->x, b.ln1_w, b.ln1_b, c.enc_ln_eps, Bc, 64, D, win, xin, st));
+      CKS(launch_layernorm(h->x, b.ln1_w, b.ln1_b, c.enc_ln_eps, Bc, 64, D, 0, h->xn_t, st));
       mark(h, PC_LN, st);
     }
-    {  // qkv + head split
-      GemmParams p = gp(Mq, 3 * D, D);
-      p.bias = b.qkv_b; p.q = h->q; p.k = h->k; p.v = h->v; p.T = T; p.heads = heads;
-      CKS(launch_gemm(EPI_QKV, xin, b.qkv_w, p, sms, st));
+    {  // qkv + head split (+ window_partition)
+      GemmParams p = gp(tok, 3 * D, D);
+      p.bias = b.qkv_b; p.q = h->q; p.k = h->k; p.v = h->v; p.T = T; p.heads = heads; p.ln_partition = win ? 1 : 0;
+      CKS(launch_gemm(EPI_QKV, h->xn_t, b.qkv_w, p, sms, st));
       mark(h, PC_GEMM_QKV, st);
     }
     // attention (+ rel-pos bias, + window_unpartition)
@@ -598,7 +598,7 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
       if (fuse_next) {
         const EncBlock& nb = h->blocks[i + 1];
         p.ln_w = nb.ln1_w; p.ln_b = nb.ln1_b; p.ln_eps = c.enc_ln_eps;
-        p.out2 = nb.global ? h->xn_t : h->xn; p.ln_partition = nb.global ? 0 : 1;
+        p.out2 = h->xn_t; p.ln_partition = 0;
       }
       CKS(launch_gemm(fuse_next ? EPI_RES_LN : EPI_RES_F32, h->hid, b.lin2_w, p, sms, st));
       mark(h, PC_GEMM_LIN2, st);
@@ -646,10 +646,19 @@ int t2i_block(ullsam_handle* h, int R, int Nt, const float* q_w, const float* q_
 
 // TwoWayTransformer.forward (transformer.py:62-108).  On entry h->tokens = point_embedding, h->keys(_bf) = image tokens,
 // h->pe_bf = image_pe tokens.  On exit h->queries / h->keys(_bf) hold the outputs.
-int transformer_run(ullsam_handle* h, int R, int Nt, cudaStream_t st) {
+// with_heads: also run the hypernetwork MLPs and the IoU head (h->hyper, h->iou4), mask_decoder.py:136-148.
+bool dec_fused_enabled(const ullsam_handle* h, int Nt) {
+  static const bool off = getenv("ULLSAM_DEC_FUSED") != nullptr && atoi(getenv("ULLSAM_DEC_FUSED")) == 0;
+  return !off && h->cfg.iou_head_depth <= 4 && dec_tokens_fused_supported(Nt, h->cfg.dec_mlp_dim, h->cfg.iou_head_hidden);
+}
+
+int heads_run(ullsam_handle* h, int R, int Nt, cudaStream_t st);
+
+int transformer_run(ullsam_handle* h, int R, int Nt, cudaStream_t st, bool with_heads) {
   const auto& c = h->cfg;
   const int sms = h->sms, M = R * Nt, rk = R * 4096;
   CKC(cudaMemcpyAsync(h->queries, h->tokens, static_cast<size_t>(M) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const bool fused = dec_fused_enabled(h, Nt);
   // (image_pe) x [Wk ; 0 ; Wq]^T for every layer: the "+ key_pe" of transformer.py:167,179 folded into the projections
   for (int i = 0; i <= c.dec_depth; ++i) {
     const bool fin = (i == c.dec_depth);
@@ -657,6 +666,52 @@ int transformer_run(ullsam_handle* h, int R, int Nt, cudaStream_t st) {
     p.out = h->peproj[i];
     CKS(launch_gemm(EPI_F32, h->pe_bf, fin ? h->fin_catpe_w : h->layers[i].catpe_w, p, sms, st));
     mark(h, PC_DEC_GEMM, st, 1);
+  }
+  if (fused) {
+    // token side of each block as one cluster kernel (decoder_fused.cu); image side as before
+    for (int i = 0; i < c.dec_depth; ++i) {
+      const DecLayer& L = h->layers[i];
+      {
+        GemmParams p = gp(rk, 384, 256);
+        p.bias = L.cat_b; p.out = h->proj; p.pos = h->peproj[i]; p.pos_rows = 4096;
+        CKS(launch_gemm(EPI_BF16, h->keys_bf, L.cat_w, p, sms, st));
+        mark(h, PC_DEC_GEMM, st, 1);
+      }
+      DecTokLayer w{};
+      w.sq_w = L.self.q_w; w.sq_b = L.self.q_b; w.sk_w = L.self.k_w; w.sk_b = L.self.k_b;
+      w.sv_w = L.self.v_w; w.sv_b = L.self.v_b; w.so_w = L.self.o_w; w.so_b = L.self.o_b;
+      w.n1_w = L.n1_w; w.n1_b = L.n1_b; w.n2_w = L.n2_w; w.n2_b = L.n2_b; w.n3_w = L.n3_w; w.n3_b = L.n3_b;
+      w.tq_w = L.t2i_q_w; w.tq_b = L.t2i_q_b; w.to_w = L.t2i_o_w; w.to_b = L.t2i_o_b;
+      w.m1_w = L.mlp1_w; w.m1_b = L.mlp1_b; w.m2_w = L.mlp2_w; w.m2_b = L.mlp2_b;
+      w.ik_w = L.i2t_k_w; w.ik_b = L.i2t_k_b; w.iv_w = L.i2t_v_w; w.iv_b = L.i2t_v_b;
+      w.mlp_dim = c.dec_mlp_dim; w.skip_pe = (i == 0);
+      CKS(launch_dec_token_layer(w, h->queries, h->tokens, h->proj, 384, R, Nt, h->k128, h->v128, st));
+      mark(h, PC_DEC_TOKENS, st, 1);
+      CKS(launch_i2t_attention(h->proj, 384, 256, h->k128, h->v128, R, Nt, h->ao128, st));
+      mark(h, PC_DEC_ATTN, st, 1);
+      {
+        GemmParams p = gp(rk, 256, 128);
+        p.bias = L.i2t_o_b; p.residual = h->keys; p.out = h->keys; p.out2 = h->keys_bf;
+        p.ln_w = L.n4_w; p.ln_b = L.n4_b; p.ln_eps = 1e-5f;
+        CKS(launch_gemm(EPI_LN_RES, h->ao128, L.i2t_o_w, p, sms, st));
+        mark(h, PC_DEC_GEMM, st, 1);
+      }
+    }
+    {
+      GemmParams p = gp(rk, 256, 256);
+      p.bias = h->fin_cat_b; p.out = h->proj; p.pos = h->peproj[c.dec_depth]; p.pos_rows = 4096;
+      CKS(launch_gemm(EPI_BF16, h->keys_bf, h->fin_cat_w, p, sms, st));
+      mark(h, PC_DEC_GEMM, st, 1);
+    }
+    DecTokFinal f{};
+    f.tq_w = h->fin_q_w; f.tq_b = h->fin_q_b; f.to_w = h->fin_o_w; f.to_b = h->fin_o_b; f.nf_w = h->nf_w; f.nf_b = h->nf_b;
+    f.hyp_w0 = h->hyp_w0; f.hyp_b0 = h->hyp_b0; f.hyp_w1 = h->hyp_w1; f.hyp_b1 = h->hyp_b1; f.hyp_w2 = h->hyp_w2; f.hyp_b2 = h->hyp_b2;
+    for (int i = 0; i < c.iou_head_depth; ++i) { f.iou_w[i] = h->iou_w[i]; f.iou_b[i] = h->iou_b[i]; }
+    f.iou_depth = c.iou_head_depth; f.iou_hidden = c.iou_head_hidden;
+    CKS(launch_dec_token_final(f, h->queries, h->tokens, h->proj, 256, R, Nt, with_heads ? h->hyper : nullptr,
+                               with_heads ? h->iou4 : nullptr, st));
+    mark(h, PC_DEC_TOKENS, st, 1);
+    return ULLSAM_OK;
   }
   for (int i = 0; i < c.dec_depth; ++i) {
     const DecLayer& L = h->layers[i];
@@ -712,30 +767,13 @@ int transformer_run(ullsam_handle* h, int R, int Nt, cudaStream_t st) {
     mark(h, PC_DEC_GEMM, st, 1);
     if (int rc = t2i_block(h, R, Nt, h->fin_q_w, h->fin_q_b, h->fin_o_w, h->fin_o_b, h->nf_w, h->nf_b, 256, st)) return rc;
   }
-  return ULLSAM_OK;
+  return with_heads ? heads_run(h, R, Nt, st) : ULLSAM_OK;
 }
 
-// MaskDecoder.predict_masks (mask_decoder.py:112-149) writing mask channels [m0, m0+cnt)
-int decoder_run(ullsam_handle* h, const float* emb, int n_img, const float* image_pe, const float* sparse, int P, int Ns,
-                const float* dense, int dense_mode, int dense_batch, int m0, int cnt, float* masks, float* iou,
-                cudaStream_t st) {
+// hypernetwork MLPs on the 4 mask tokens (grouped) and the IoU head on token 0, launch-per-op path (mask_decoder.py:136-148)
+int heads_run(ullsam_handle* h, int R, int Nt, cudaStream_t st) {
   const auto& c = h->cfg;
-  if (int rc = check_ready(h, 1)) return rc;
-  if (int rc = check_ready(h, 2)) return rc;
-  if (n_img <= 0 || P <= 0 || Ns < 0) return fail(h, ULLSAM_ERR_INVALID, "decoder: n_img, P must be positive");
-  const int R = n_img * P, nm = c.num_mask_tokens, Nt = 1 + nm + Ns, sms = h->sms;
-  if (Nt > 64) return fail(h, ULLSAM_ERR_INVALID, "decoder: more than 64 prompt tokens per prompt is not supported");
-  if (dense_batch != 1 && dense_batch != R) return fail(h, ULLSAM_ERR_INVALID, "decoder: dense batch must be 1 or n_img*P");
-  if (nm != 4) return fail(h, ULLSAM_ERR_INVALID, "decoder: num_mask_tokens must be 4");
-  if (int rc = ensure_decoder_ws(h, R, Nt)) return rc;
-  CKS(launch_tok_init(h->iou_token, h->mask_tokens, nm, sparse, Ns, R, h->tokens, st));
-  mark(h, PC_DEC_TOKENS, st, 1);
-  CKS(launch_keys_init(emb, R, P, dense, dense_mode, dense_batch, h->keys, h->keys_bf, st));
-  mark(h, PC_DEC_TOKENS, st, 1);
-  CKS(launch_keys_init(image_pe, 1, 1, nullptr, 0, 1, nullptr, h->pe_bf, st));
-  mark(h, PC_DEC_TOKENS, st, 1);
-  if (int rc = transformer_run(h, R, Nt, st)) return rc;
-  // hypernetwork MLPs on the 4 mask tokens (grouped) and the IoU head on token 0
+  const int nm = c.num_mask_tokens;
   {
     TokLinear a = lin(h->queries + 256, nullptr, h->hyp_w0, h->hyp_b0, nullptr, h->hyp1, R, 256, 256, 2);
     a.G = nm; a.ldx = Nt * 256; a.x_gs = 256; a.w_gs = 256 * 256; a.b_gs = 256; a.y_gs = static_cast<size_t>(R) * 256;
@@ -765,6 +803,31 @@ int decoder_run(ullsam_handle* h, const float* emb, int n_img, const float* imag
       x = y;
       ldx = N;
     }
+  }
+  return ULLSAM_OK;
+}
+
+// MaskDecoder.predict_masks (mask_decoder.py:112-149) writing mask channels [m0, m0+cnt)
+int decoder_run(ullsam_handle* h, const float* emb, int n_img, const float* image_pe, const float* sparse, int P, int Ns,
+                const float* dense, int dense_mode, int dense_batch, int m0, int cnt, float* masks, float* iou,
+                cudaStream_t st) {
+  const auto& c = h->cfg;
+  if (int rc = check_ready(h, 1)) return rc;
+  if (int rc = check_ready(h, 2)) return rc;
+  if (n_img <= 0 || P <= 0 || Ns < 0) return fail(h, ULLSAM_ERR_INVALID, "decoder: n_img, P must be positive");
+  const int R = n_img * P, nm = c.num_mask_tokens, Nt = 1 + nm + Ns, sms = h->sms;
+  if (Nt > 64) return fail(h, ULLSAM_ERR_INVALID, "decoder: more than 64 prompt tokens per prompt is not supported");
+  if (dense_batch != 1 && dense_batch != R) return fail(h, ULLSAM_ERR_INVALID, "decoder: dense batch must be 1 or n_img*P");
+  if (nm != 4) return fail(h, ULLSAM_ERR_INVALID, "decoder: num_mask_tokens must be 4");
+  if (int rc = ensure_decoder_ws(h, R, Nt)) return rc;
+  CKS(launch_tok_init(h->iou_token, h->mask_tokens, nm, sparse, Ns, R, h->tokens, st));
+  mark(h, PC_DEC_TOKENS, st, 1);
+  CKS(launch_keys_init(emb, R, P, dense, dense_mode, dense_batch, h->keys, h->keys_bf, st));
+  mark(h, PC_DEC_TOKENS, st, 1);
+  CKS(launch_keys_init(image_pe, 1, 1, nullptr, 0, 1, nullptr, h->pe_bf, st));
+  mark(h, PC_DEC_TOKENS, st, 1);
+  if (int rc = transformer_run(h, R, Nt, st, true)) return rc;
+  {
     CKS(launch_slice_copy(h->iou4, R, nm, m0, cnt, 1, iou, st));
     mark(h, PC_DEC_TOKENS, st, 1);
   }
@@ -1005,7 +1068,7 @@ int ullsam_transformer_forward(ullsam_handle* h, const void* image_embedding, in
   mark(h, PC_DEC_TOKENS, st, 1);
   CKS(launch_keys_init(static_cast<const float*>(image_pe), 1, 1, nullptr, 0, 1, nullptr, h->pe_bf, st));
   mark(h, PC_DEC_TOKENS, st, 1);
-  if (int rc = transformer_run(h, R, Nt, st)) return rc;
+  if (int rc = transformer_run(h, R, Nt, st, false)) return rc;
   CKC(cudaMemcpyAsync(queries, h->queries, static_cast<size_t>(R) * Nt * 256 * 4, cudaMemcpyDeviceToDevice, st));
   CKC(cudaMemcpyAsync(keys, h->keys, static_cast<size_t>(R) * 4096 * 256 * 4, cudaMemcpyDeviceToDevice, st));
   return ULLSAM_OK;

@@ -84,6 +84,7 @@ def gemm(
     if epi == _lib.EPI_QKV:
         q, k, v = qkv
         d.q, d.k, d.v, d.T, d.heads = ptr(q), ptr(k), ptr(v), T, heads
+        # ln_partition: A's rows are image tokens [B,64,64]; the store window-partitions them (pad rows not written)
     else:
         if out is None:
             if epi in (_lib.EPI_BF16, _lib.EPI_LN_BF16):
