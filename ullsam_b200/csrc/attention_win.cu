@@ -28,6 +28,9 @@
 #include "common.cuh"
 #include "gemm.h"
 
+#ifndef ULLSAM_WIN_DEFER
+#define ULLSAM_WIN_DEFER 1
+#endif
 #ifndef ULLSAM_WIN_TIMELINE
 #define ULLSAM_WIN_TIMELINE 0
 #endif
@@ -53,12 +56,12 @@ struct W {
   static constexpr int OFF_Q = 0;                      // [128 x 64] + [72 x 64] bf16
   static constexpr int OFF_K = 16384 + Q1_ROWS * 128;  // 7 x [32 x 64] bf16
   static constexpr int OFF_V = OFF_K + NT * TILE_BYTES;
-  static constexpr int OFF_TABW = OFF_V + 5 * TILE_BYTES;   // the two 4 KB tables ride in V tiles 5 and 6 until the bias MMAs retire
-  static constexpr int OFF_TABH = OFF_V + 6 * TILE_BYTES;
+  static constexpr int OFF_TABW = OFF_V + 0 * TILE_BYTES;   // the two 4 KB tables ride in V tiles 0 and 1 until the bias MMAs retire
+  static constexpr int OFF_TABH = OFF_V + 1 * TILE_BYTES;
   static constexpr int OFF_SCR = OFF_V + NT * TILE_BYTES;   // fp32 [14][256]: rel_h of every row
   static constexpr int OFF_SCRW = OFF_SCR + 14 * 256 * 4;   // fp32 [14][256]: rel_w of every row
   static constexpr int OFF_BAR = OFF_SCRW + 14 * 256 * 4;
-  static constexpr int NBAR = 2 + 2 * NT + 3 * 2 * NT + 2;
+  static constexpr int NBAR = 2 + 2 * NT + 3 * 2 * NT + 2 + 2;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 256;                // per query tile: S/P slots [0,32) [32,64), O (tables first) [64,128)
 };
@@ -87,12 +90,18 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   uint64_t* p_ready = s_full + 2 * NT; // [qt][NT]
   uint64_t* o_done = p_ready + 2 * NT; // [qt][NT]
   uint64_t* epi_done = o_done + 2 * NT; // [qt]: the query tile's softmax warps have drained O (the next item's tables may land)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_done + 2);
+  uint64_t* tab_done = epi_done + 2;    // [qt]: this query tile's bias-table MMAs have retired (its softmax warps may gather)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tab_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Persistent CTA: items (window * heads + head) blockIdx.x, blockIdx.x + gridDim.x, ...  Every mbarrier completes exactly
   // one phase per item, so the wait parity of item number `it` is simply it & 1 and nothing is ever re-initialised.
-  auto issue_loads = [&](int gh) {   // Q, the bias tables, all K tiles and V tiles 0..4 of one item (one elected lane)
+  // Q, the bias tables, all K tiles and V tiles 2..4 of one item (one elected lane).  These regions are dead once the LAST
+  // QK MMA of the previous item has retired (Q and K feed only the QK MMAs; V(t) is dead after PV(t); the table slots V0 / V1
+  // after PV(1)), i.e. two key tiles before that item ends — so the loads of the next item are issued there and their latency
+  // (~2 K cycles, which used to sit between two items with nothing else to do) is hidden under the last two softmax rounds.
+  // V0, V1 (table slots) and V5, V6 (in use until the previous item's last PV) follow once the bias MMAs have retired.
+  auto issue_loads = [&](int gh) {
     const int row_base = gh * W::T;
     mbar_arrive_expect_tx(q_full, 16384 + W::Q1_ROWS * 128 + 2 * 4096);
     tma_load_2d(smem + W::OFF_Q, &tmQ, q_full, 0, row_base);
@@ -105,7 +114,7 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       tma_load_2d(smem + W::OFF_K + t * W::TILE_BYTES, &tmK, &k_full[t], 0, row_base + t * W::TK);
     }
 #pragma unroll
-    for (int t = 0; t < 5; ++t) {
+    for (int t = 2; t < 5; ++t) {
       mbar_arrive_expect_tx(&v_full[t], W::TILE_BYTES);
       tma_load_2d(smem + W::OFF_V + t * W::TILE_BYTES, &tmV, &v_full[t], 0, row_base + t * W::TK);
     }
@@ -119,6 +128,8 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       for (int i = 0; i < 2 * NT; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_done[i], 1); }
       mbar_init(&epi_done[0], 4);
       mbar_init(&epi_done[1], 4);
+      mbar_init(&tab_done[0], 1);
+      mbar_init(&tab_done[1], 1);
       fence_barrier_init();
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmQ1); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
       issue_loads(blockIdx.x);
@@ -157,15 +168,18 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         for (int k = 0; k < 4; ++k) umma_ss(tq0 + 64, dq + 2 * k, drw + 2 * k, idesc_rel, k != 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_ss(tq0 + 96, dq + 2 * k, drh + 2 * k, idesc_rel, k != 0);
-        umma_commit(pro_done);
+        umma_commit(&tab_done[qt]);   // to this query tile's softmax warps (the two tiles' chains stay independent)
+        umma_commit(pro_done);        // to the TMA warp: both tiles' table reads have retired, V0 / V1 may land
       }
       __syncwarp();
       if (warp == 8) {
-        // V tiles 5, 6 share their slots with the tables: load them once BOTH warps' bias MMAs have retired
+        // V tiles 0, 1 share their slots with the tables, V tiles 5, 6 were in use until the previous item's last PV: load
+        // them once BOTH warps' bias MMAs have retired (each warp issued them after its epi_done, i.e. after its last PV)
         mbar_wait(pro_done, ph);
         if (leader) {
 #pragma unroll
-          for (int t = 5; t < NT; ++t) {
+          for (int t = 0; t < NT; ++t) {
+            if (t >= 2 && t < 5) continue;
             mbar_arrive_expect_tx(&v_full[t], W::TILE_BYTES);
             tma_load_2d(smem + W::OFF_V + t * W::TILE_BYTES, &tmV, &v_full[t], 0, gh * W::T + t * W::TK);
           }
@@ -200,14 +214,14 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         __syncwarp();
         // the slot of tile t is free once PV(t) has read P(t); tcgen05 ops of one thread execute in order
         if (t + 2 < NT) issue_qk(t + 2);
-      }
-      if (warp == 8 && gh + static_cast<int>(gridDim.x) < nitems) {
-        // every MMA of this item has retired (both query tiles): shared memory is free, the next item's loads overlap the
-        // epilogue of this one
-        mbar_wait(&o_done[0 * NT + NT - 1], ph);
-        mbar_wait(&o_done[1 * NT + NT - 1], ph);
-        if (leader) issue_loads(gh + gridDim.x);
-        __syncwarp();
+        if (t + 2 == NT - 1 && warp == 8 && gh + static_cast<int>(gridDim.x) < nitems) {
+          // the last QK of both query tiles has retired (and with it, in issue order, every earlier QK and PV(0..4)): Q, K,
+          // V2..4 and the table slots are free — the next item's loads start now
+          mbar_wait(&s_full[0 * NT + NT - 1], ph);
+          mbar_wait(&s_full[1 * NT + NT - 1], ph);
+          if (leader) issue_loads(gh + gridDim.x);
+          __syncwarp();
+        }
       }
     }
   } else {
@@ -230,7 +244,7 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     for (int it = 0, gh = blockIdx.x; gh < nitems; ++it, gh += gridDim.x) {
     const uint32_t ph = it & 1;
     // ---- bias rows: w[kw] = Tw[row][qw - kw + 13] (registers), h[kh] = Th[row][qh - kh + 13] (shared memory) ----
-    mbar_wait(pro_done, ph);
+    mbar_wait(&tab_done[qt], ph);
     tc_fence_after();
     WTL(0);
     {
@@ -240,6 +254,8 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       tmem_ld32(tbase + 64, v);
       tmem_ld32(tbase + 96, v2);
       tmem_wait_ld();
+      // (a branch-free variant — unconditional stores whose ADDRESS is selected, misses parked in a dummy word — was
+      //  measured slower here: 0.426 vs 0.411 ms per launch; only 28 of the 54 entries are stored this way)
 #pragma unroll
       for (int i = 0; i < 27; ++i) {
         const int kk = qw + 13 - i;
@@ -276,6 +292,14 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       const uint32_t s_addr = tbase + (t & 1) * 32;
       uint32_t v[32];
       tmem_ld32(s_addr, v);
+      if (ULLSAM_WIN_DEFER && t > 0) {
+        // hand P(t-1) over only now: the completion of its tcgen05.st overlaps the tensor-memory read of this tile (the
+        // tensor core is a slot ahead, S(t) has long been there, so P(t-1) is not urgent; the round trip of the store is)
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[qt * NT + t - 1]);
+      }
       tmem_wait_ld();
       // ---- biased scores (log2 units) of the 28 keys of the tile and their exact maximum ----
       float x[28];
@@ -325,10 +349,12 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       pk[15] = 0u;
       tmem_st16(s_addr, pk);
       WTL(5);
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[qt * NT + t]);
+      if (!ULLSAM_WIN_DEFER || t == NT - 1) {
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[qt * NT + t]);
+      }
       WTL(6);
     }
 
@@ -336,11 +362,6 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     mbar_wait(&o_done[qt * NT + NT - 1], ph);
     tc_fence_after();
     WTL(7);
-#if ULLSAM_WIN_TIMELINE
-    if (blockIdx.x == 300 && lane == 0 && quad == 0)
-      printf("win qt %d: wait tables %lld | gather %lld | per tile: wait S %lld, ld+bias+max %lld, rescale %lld, exp %lld, st+arrive %lld | wait last PV %lld | total %lld (since kernel start %lld)\n",
-             qt, wtl[0], wtl[1], wtl[2] / NT, wtl[3] / NT, wtl[4] / NT, wtl[5] / NT, wtl[6] / NT, wtl[7], clock64() - wtl_begin, clock64() - wtl_begin);
-#endif
     const float inv_l = 1.0f / (l0 + l1);
     long out_row = -1;
     if (tq < W::T) {
@@ -373,6 +394,14 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       }
     }
     }  // item loop
+#if ULLSAM_WIN_TIMELINE
+    if (blockIdx.x == 100 && lane == 0 && quad == 0) {
+      const int nit = (nitems - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+      printf("win qt %d, %d items, per item: wait tables %lld | gather %lld | per tile: wait S %lld, ld+bias+max %lld, rescale %lld, exp %lld, st+arrive %lld | wait last PV + epilogue %lld | total per item %lld\n",
+             qt, nit, wtl[0] / nit, wtl[1] / nit, wtl[2] / nit / NT, wtl[3] / nit / NT, wtl[4] / nit / NT, wtl[5] / nit / NT,
+             wtl[6] / nit / NT, wtl[7] / nit, (clock64() - wtl_begin) / nit);
+    }
+#endif
   }
 
   tc_fence_before();
