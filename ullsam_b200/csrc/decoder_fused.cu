@@ -21,12 +21,14 @@
 #ifndef ULLSAM_DEC_TIMELINE
 #define ULLSAM_DEC_TIMELINE 0
 #endif
-#if ULLSAM_DEC_TIMELINE
-#define DT_STAMP(name) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.y == 3) { const long long t_ = clock64(); printf("  rank %d %-18s %8lld\n", rank, name, t_ - dt_last); dt_last = t_; } } while (0)
-#define DT_BEGIN long long dt_last = clock64()
+#if ULLSAM_DEC_TIMELINE   // debug builds (tools/build_variant.sh): per-phase cycle counts of one CTA, printed once at the end
+#define DT_STAMP(name) do { __syncthreads(); if (dt_n < 16) { const long long t_ = clock64(); dt_name[dt_n] = name; dt_t[dt_n++] = t_ - dt_last; dt_last = clock64(); } } while (0)
+#define DT_BEGIN long long dt_last = clock64(); long long dt_t[16]; const char* dt_name[16]; int dt_n = 0
+#define DT_END do { if (threadIdx.x == 0 && blockIdx.y == 3 && rank == 1) for (int i_ = 0; i_ < dt_n; ++i_) printf("  %-16s %8lld\n", dt_name[i_], dt_t[i_]); } while (0)
 #else
 #define DT_STAMP(name) do { } while (0)
 #define DT_BEGIN do { } while (0)
+#define DT_END do { } while (0)
 #endif
 
 namespace ullsam {
@@ -37,10 +39,11 @@ constexpr int FT = 512;        // threads per CTA
 constexpr int FW = FT / 32;    // warps
 constexpr int CL = 4;          // CTAs per prompt
 constexpr int E = 256;         // transformer width
-constexpr int T2I_TG = 4;      // tokens per pass of the token->image attention
+constexpr int T2I_KEYS = 128;  // keys per staged K / V block of the token->image attention
+constexpr int T2I_STAGE_FLOATS = 2 * 2 * T2I_KEYS * 16 / 2;   // K and V of this CTA's two heads, bf16: 16 KB = 4096 floats
 // floats per token row in shared memory: Bq, Bpe, Bqp, Ba (aliased by the MLP partial), By: 5 x 256; Lq/Lk/Lv: 3 x 64; hid: 512
 constexpr int ROW_FLOATS = 5 * E + 3 * 64 + 512;
-constexpr int FIXED_FLOATS = 2 * T2I_TG * 16 + 2 * 8 * T2I_TG * 18;   // t2i: q of the pass, per-warp partial results
+constexpr int FIXED_FLOATS = 2 * 8 * 8 * 18;   // t2i: per-warp partial results [head][warp][token lane][max, sum, acc[16]]
 
 ULLSAM_DEVICE void st_cluster(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
@@ -78,25 +81,39 @@ ULLSAM_DEVICE void reduce8(float (&a)[8], int lane) {
 // y[r][c] = sum_k xs[r][k] * W[c][k] for the 8 rows at xs (row stride ldx floats) and columns c in [0, ncols) of the
 // row-major matrix W (row stride ldw floats, K a multiple of 128); emit(r, c, value) is called by ONE lane per (r, c).
 // A warp takes two columns at a time: the lanes split K in float4 steps (coalesced weight reads, conflict-free x reads).
-template <class Emit>
-ULLSAM_DEVICE void gemv8(const float* xs, int ldx, int K, const float* __restrict__ W, int ldw, int ncols, int warp, int lane,
+// (K is a template parameter: the weight loads of a column pair — K / 64 float4 per lane — are all issued before the first
+//  FMA, and the next pair's loads are issued before this pair is reduced: the loop is a chain of L2 round trips otherwise.)
+template <int K, class Emit>
+ULLSAM_DEVICE void gemv8(const float* xs, int ldx, const float* __restrict__ W, int ldw, int ncols, int warp, int lane,
                          Emit emit) {
-  for (int c = 2 * warp; c < ncols; c += 2 * FW) {
+  constexpr int KI = K / 128;
+  float4 u[KI], v[KI];
+  auto load_pair = [&](int c) {
     const int c1 = (c + 1 < ncols) ? c + 1 : c;
     const float4* w0 = reinterpret_cast<const float4*>(W + static_cast<size_t>(c) * ldw);
     const float4* w1 = reinterpret_cast<const float4*>(W + static_cast<size_t>(c1) * ldw);
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      u[i] = __ldg(w0 + lane + 32 * i);
+      v[i] = __ldg(w1 + lane + 32 * i);
+    }
+  };
+  if (2 * warp < ncols) load_pair(2 * warp);
+  for (int c = 2 * warp; c < ncols; c += 2 * FW) {
+    const int c1 = (c + 1 < ncols) ? c + 1 : c;
     float a0[8], a1[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) a0[r] = a1[r] = 0.f;
-    for (int k4 = lane; k4 < K / 4; k4 += 32) {
-      const float4 u = __ldg(w0 + k4), v = __ldg(w1 + k4);
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        const float4 x = *reinterpret_cast<const float4*>(xs + r * ldx + 4 * k4);
-        a0[r] = fmaf(x.x, u.x, fmaf(x.y, u.y, fmaf(x.z, u.z, fmaf(x.w, u.w, a0[r]))));
-        a1[r] = fmaf(x.x, v.x, fmaf(x.y, v.y, fmaf(x.z, v.z, fmaf(x.w, v.w, a1[r]))));
+        const float4 x = *reinterpret_cast<const float4*>(xs + r * ldx + 4 * (lane + 32 * i));
+        a0[r] = fmaf(x.x, u[i].x, fmaf(x.y, u[i].y, fmaf(x.z, u[i].z, fmaf(x.w, u[i].w, a0[r]))));
+        a1[r] = fmaf(x.x, v[i].x, fmaf(x.y, v[i].y, fmaf(x.z, v[i].z, fmaf(x.w, v[i].w, a1[r]))));
       }
     }
+    if (c + 2 * FW < ncols) load_pair(c + 2 * FW);   // in flight during the reduction and the emit
     reduce8(a0, lane);
     reduce8(a1, lane);
     if ((lane & 3) == 0) {
@@ -124,7 +141,7 @@ ULLSAM_DEVICE void gemv1(const float* xs, int K, const float* __restrict__ W, in
 }
 
 struct Smem {
-  float *Bq, *Bpe, *Bqp, *Ba, *By, *Lq, *Lk, *Lv, *hid, *part, *qs, *red;
+  float *Bq, *Bpe, *Bqp, *Ba, *By, *Lq, *Lk, *Lv, *hid, *part, *red, *stage;
 };
 
 // value -> the same location of all four CTAs of the cluster
@@ -164,103 +181,173 @@ ULLSAM_DEVICE void layer_norm_rows(const Smem& s, const float* __restrict__ gamm
 // tokens -> image attention (transformer.py:165-170 / :101-106), internal width 128 = 8 heads x 16, followed by the
 // output projection, the residual add and the LayerNorm.  CTA `rank` owns heads 2 rank, 2 rank + 1.
 //   q = (queries + pe) Wq^T + bq;  o = softmax(q K^T / 4) V;  queries = LN(queries + o Wo^T + bo)
-// K, V: bf16 columns [0,128) / [128,256) of kv[4096][ldkv] (this prompt's rows).  Thread halves 0..255 / 256..511 take one
-// head each: the 4096 keys are spread over the 256 threads, each keeps an online softmax for up to TG tokens per pass.
-ULLSAM_DEVICE void t2i_block(const Smem& s, int rank, int nt, int nr, const float* __restrict__ q_w, const float* __restrict__ q_b,
-                             const float* __restrict__ o_w, const float* __restrict__ o_b, const float* __restrict__ n_w,
-                             const float* __restrict__ n_b, const __nv_bfloat16* __restrict__ kv, int ldkv, int warp, int lane) {
-  constexpr int TG = T2I_TG;
-  // q slice: columns [32 rank, 32 rank + 32), scaled by 1/sqrt(16)
-  for (int rb = 0; rb < nr; rb += 8)
-    gemv8(s.Bqp + rb * E, E, E, q_w + static_cast<size_t>(32 * rank) * E, E, 32, warp, lane,
-          [&](int r, int c, float v) { s.Lq[(rb + r) * 64 + c] = (v + __ldg(q_b + 32 * rank + c)) * 0.25f; });
-  __syncthreads();
-  const int hh = threadIdx.x >> 8, t = threadIdx.x & 255;     // local head, thread inside the half
-  const int head = 2 * rank + hh, hw = warp & 7;
-  float* qs = s.qs + hh * TG * 16;
-  float* red = s.red + hh * 8 * TG * 18;
-  for (int i0 = 0; i0 < nt; i0 += TG) {
-    const int ng = (nt - i0 < TG) ? (nt - i0) : TG;
-    __syncthreads();
-    if (t < TG * 16) {
-      const int i = t >> 4, d = t & 15;
-      qs[i * 16 + d] = (i < ng) ? s.Lq[(i0 + i) * 64 + hh * 16 + d] : 0.f;
-    }
-    __syncthreads();
-    float m[TG], l[TG], acc[TG][16];
+// K, V: bf16 columns [0,128) / [128,256) of kv[4096][ldkv] (this prompt's rows); this CTA needs 64 + 64 bytes of each row.
+// They are STAGED: blocks of 128 keys (16 KB) travel global -> shared memory with cp.async through a ring of `ns` buffers, so
+// ~100 KB per SM are in flight and the loop runs from shared memory (the first version loaded K / V into registers one key
+// per thread and iteration and spent 110 us per call waiting for them; a second, SIMT one from shared memory still needed
+// ~55 us: 8 token lanes repeated the bf16 -> fp32 conversion of every key).  ONE pass over the keys serves all tokens.
+// NG = number of 16-token tiles (1 for up to 16 tokens, 2 for up to 24).
+template <int NG>
+ULLSAM_DEVICE void t2i_attention(const Smem& s, int rank, int nt, int nr, const __nv_bfloat16* __restrict__ kv, int ldkv, int ns,
+                                 int warp, int lane) {
+  constexpr int NBLK = 4096 / T2I_KEYS;
+  const int t = threadIdx.x;
+  // ---- producer side: every thread copies two 16-byte chunks per block ----
+  auto issue = [&](int blk) {
+    uint8_t* stage = reinterpret_cast<uint8_t*>(s.stage + (blk % ns) * T2I_STAGE_FLOATS);
 #pragma unroll
-    for (int i = 0; i < TG; ++i) {
-      m[i] = -INFINITY;
-      l[i] = 0.f;
-#pragma unroll
-      for (int d = 0; d < 16; ++d) acc[i][d] = 0.f;
+    for (int i = 0; i < 2; ++i) {
+      const int c = t + FT * i;                 // 1024 chunks: [K | V][128 keys][2 heads][2 halves of 16 bytes]
+      const int isv = c >> 9, idx = c & 511, key = idx >> 2, hl = (idx >> 1) & 1, part = idx & 1;
+      const __nv_bfloat16* src = kv + static_cast<size_t>(blk * T2I_KEYS + key) * ldkv + isv * 128 + (2 * rank + hl) * 16 + part * 8;
+      const uint32_t dst = smem_u32(stage + isv * 8192 + hl * 4096 + key * 32 + part * 16);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int b = 0; b < ns - 1; ++b) issue(b);
+  // ---- consumer side: warp-level tensor-core MMAs (mma.sync m16n8k16, bf16 operands, fp32 accumulate) ----
+  // Warps 0..7 serve head 2 rank, warps 8..15 head 2 rank + 1; warp w of a head takes keys [16 w, 16 w + 16) of every staged
+  // block.  Per 16-key chunk and 16-token tile:  S = Q K^T (A = Q split into bf16 hi + lo parts so the fp32 queries lose
+  // nothing, B = K^T straight from the staged rows), online softmax on the accumulator fragment (a token row lives in the
+  // four lanes of a quad), O += P V (A = the P fragment re-packed as bf16, B = V through ldmatrix.trans).
+  const int hh = warp >> 3, hw = warp & 7, g = lane >> 2, tq = lane & 3;
+  uint32_t qhi[NG][4], qlo[NG][4];
+  float m[NG][2], l[NG][2], o[NG][2][4];   // rows g and g + 8 of tile mt; o[mt][dim tile][c0..c3]
+#pragma unroll
+  for (int mt = 0; mt < NG; ++mt) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = mt * 16 + g + (i & 1) * 8, d = 2 * tq + (i >> 1) * 8;   // a0: (g, 2tq) a1: (g+8, 2tq) a2: (g, 2tq+8) a3: (g+8, 2tq+8)
+      const bool live = row < nr;   // (a 16-row tile may reach past the rows held in shared memory: padding tokens)
+      const float x0 = live ? s.Lq[row * 64 + hh * 16 + d] : 0.f, x1 = live ? s.Lq[row * 64 + hh * 16 + d + 1] : 0.f;
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+      qhi[mt][i] = pack_bf16(__bfloat162float(h0), __bfloat162float(h1));
+      qlo[mt][i] = pack_bf16(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      m[mt][h] = -INFINITY;
+      l[mt][h] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[mt][h][i] = 0.f;
+    }
+  }
+  auto mma = [](float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  };
 #pragma unroll 1
-    for (int jj = 0; jj < 16; ++jj) {
-      const int key = jj * 256 + t;
-      const uint4* kp = reinterpret_cast<const uint4*>(kv + static_cast<size_t>(key) * ldkv + head * 16);
-      const uint4* vp = kp + 16;  // + 128 bf16
-      const uint4 k0 = kp[0], k1 = kp[1], v0 = vp[0], v1 = vp[1];
-      float kf[16], vf[16];
-      const __nv_bfloat162* a0 = reinterpret_cast<const __nv_bfloat162*>(&k0);
-      const __nv_bfloat162* a1 = reinterpret_cast<const __nv_bfloat162*>(&k1);
-      const __nv_bfloat162* c0 = reinterpret_cast<const __nv_bfloat162*>(&v0);
-      const __nv_bfloat162* c1 = reinterpret_cast<const __nv_bfloat162*>(&v1);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float2 t0 = __bfloat1622float2(a0[u]), t1 = __bfloat1622float2(a1[u]);
-        kf[2 * u] = t0.x; kf[2 * u + 1] = t0.y; kf[8 + 2 * u] = t1.x; kf[8 + 2 * u + 1] = t1.y;
-        const float2 w0 = __bfloat1622float2(c0[u]), w1 = __bfloat1622float2(c1[u]);
-        vf[2 * u] = w0.x; vf[2 * u + 1] = w0.y; vf[8 + 2 * u] = w1.x; vf[8 + 2 * u + 1] = w1.y;
-      }
-#pragma unroll
-      for (int i = 0; i < TG; ++i) {
-        float sc = 0.f;
-#pragma unroll
-        for (int d = 0; d < 16; ++d) sc = fmaf(qs[i * 16 + d], kf[d], sc);
-        const float mn = fmaxf(m[i], sc);
-        const float corr = __expf(m[i] - mn), p = __expf(sc - mn);
-        l[i] = l[i] * corr + p;
-#pragma unroll
-        for (int d = 0; d < 16; ++d) acc[i][d] = fmaf(acc[i][d], corr, p * vf[d]);
-        m[i] = mn;
-      }
-    }
-    // merge: inside the warp first (common max, rescale, sum), then the 8 warps of the half through shared memory
-#pragma unroll
-    for (int i = 0; i < TG; ++i) {
-      const float wm = warp_max(m[i]);
-      const float sc = __expf(m[i] - wm);
-      const float ls = warp_sum(l[i] * sc);
-      if (lane == 0) { red[(hw * TG + i) * 18] = wm; red[(hw * TG + i) * 18 + 1] = ls; }
-#pragma unroll
-      for (int d = 0; d < 16; ++d) {
-        const float a = warp_sum(acc[i][d] * sc);
-        if (lane == 0) red[(hw * TG + i) * 18 + 2 + d] = a;
-      }
-    }
+  for (int blk = 0; blk < NBLK; ++blk) {
+    if (blk + ns - 1 < NBLK) issue(blk + ns - 1);
+    else asm volatile("cp.async.commit_group;" ::: "memory");   // (keeps the group count uniform)
+    // all but the newest ns - 1 groups have landed, i.e. block blk; ns is a run-time value, the wait count an immediate
+    if (ns >= 6) asm volatile("cp.async.wait_group 5;" ::: "memory");
+    else if (ns >= 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
+    else asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
-    if (t < TG * 16) {
-      const int i = t >> 4, d = t & 15;
-      if (i < ng) {
-        float gm = red[i * 18];
+    const uint8_t* stage = reinterpret_cast<const uint8_t*>(s.stage + (blk % ns) * T2I_STAGE_FLOATS);
+    const uint8_t* kb = stage + hh * 4096 + (hw * 16) * 32;          // this warp's 16 keys: K rows of 32 bytes
+    const uint8_t* vb = stage + 8192 + hh * 4096 + (hw * 16) * 32;   // V rows
+    // B fragments of K^T for the two 8-key tiles: b0 = K[key g][dims 2tq, 2tq+1], b1 = dims + 8
+    uint32_t kf[2][2];
 #pragma unroll
-        for (int w = 1; w < 8; ++w) gm = fmaxf(gm, red[(w * TG + i) * 18]);
-        float L = 0.f, A = 0.f;
+    for (int n = 0; n < 2; ++n) {
+      kf[n][0] = *reinterpret_cast<const uint32_t*>(kb + (n * 8 + g) * 32 + 4 * tq);
+      kf[n][1] = *reinterpret_cast<const uint32_t*>(kb + (n * 8 + g) * 32 + 16 + 4 * tq);
+    }
+    // B fragments of V for the two 8-dim tiles (k = the 16 keys): ldmatrix.x2.trans on rows = keys, 16 bytes = 8 dims
+    uint32_t vf[2][2];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          const float sc = __expf(red[(w * TG + i) * 18] - gm);
-          L = fmaf(red[(w * TG + i) * 18 + 1], sc, L);
-          A = fmaf(red[(w * TG + i) * 18 + 2 + d], sc, A);
+    for (int n = 0; n < 2; ++n) {
+      const uint32_t addr = smem_u32(vb + (lane & 15) * 32 + n * 16);
+      asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(vf[n][0]), "=r"(vf[n][1]) : "r"(addr));
+    }
+#pragma unroll
+    for (int mt = 0; mt < NG; ++mt) {
+      float sc[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+        mma(sc[n], qhi[mt], kf[n][0], kf[n][1]);
+        mma(sc[n], qlo[mt], kf[n][0], kf[n][1]);
+      }
+      uint32_t pa[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {   // row g (h = 0: c0, c1) and row g + 8 (h = 1: c2, c3)
+        float mx = fmaxf(fmaxf(sc[0][2 * h], sc[0][2 * h + 1]), fmaxf(sc[1][2 * h], sc[1][2 * h + 1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float mn = fmaxf(m[mt][h], mx);
+        const float corr = __expf(m[mt][h] - mn);
+        m[mt][h] = mn;
+        const float p00 = __expf(sc[0][2 * h] - mn), p01 = __expf(sc[0][2 * h + 1] - mn);
+        const float p10 = __expf(sc[1][2 * h] - mn), p11 = __expf(sc[1][2 * h + 1] - mn);
+        l[mt][h] = l[mt][h] * corr + ((p00 + p01) + (p10 + p11));   // this lane's share of the row sum
+        o[mt][0][2 * h] *= corr; o[mt][0][2 * h + 1] *= corr;
+        o[mt][1][2 * h] *= corr; o[mt][1][2 * h + 1] *= corr;
+        pa[h] = pack_bf16(p00, p01);        // a0 / a1: keys 2tq, 2tq+1 of the first key tile
+        pa[2 + h] = pack_bf16(p10, p11);    // a2 / a3: keys 8 + 2tq, ...
+      }
+      mma(o[mt][0], pa, vf[0][0], vf[0][1]);
+      mma(o[mt][1], pa, vf[1][0], vf[1][1]);
+    }
+    __syncthreads();   // the buffer is refilled by the next iteration's issue()
+  }
+  // ---- merge the 8 warps of a head through shared memory: per token row (max, sum, acc[16]) ----
+  float* red = s.red + hh * 8 * 8 * 18;   // [warp][row 0..7 of the current half-tile][18]
+#pragma unroll
+  for (int mt = 0; mt < NG; ++mt) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float ls = l[mt][h];
+      ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+      ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+      if (mt + h > 0) __syncthreads();   // the previous rows' partials have been consumed
+      float* rw = red + (hw * 8 + g) * 18;
+      if (tq == 0) { rw[0] = m[mt][h]; rw[1] = ls; }
+      rw[2 + 2 * tq] = o[mt][0][2 * h];          // dims 2tq, 2tq+1 of the first dim tile
+      rw[2 + 2 * tq + 1] = o[mt][0][2 * h + 1];
+      rw[2 + 8 + 2 * tq] = o[mt][1][2 * h];
+      rw[2 + 8 + 2 * tq + 1] = o[mt][1][2 * h + 1];
+      __syncthreads();
+      const int tl = threadIdx.x & 255;
+      if (tl < 128) {
+        const int i = tl >> 4, d = tl & 15, row = mt * 16 + h * 8 + i;
+        if (row < nt) {
+          float gm = red[i * 18];
+#pragma unroll
+          for (int w = 1; w < 8; ++w) gm = fmaxf(gm, red[(w * 8 + i) * 18]);
+          float L = 0.f, A = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            const float e = __expf(red[(w * 8 + i) * 18] - gm);
+            L = fmaf(red[(w * 8 + i) * 18 + 1], e, L);
+            A = fmaf(red[(w * 8 + i) * 18 + 2 + d], e, A);
+          }
+          bcast(s, s.Ba + row * E + (2 * rank + hh) * 16 + d, A / L);   // attention output, full 128 columns in every CTA
         }
-        bcast(s, s.Ba + (i0 + i) * E + head * 16 + d, A / L);   // attention output, full 128 columns in every CTA
       }
     }
   }
+}
+
+ULLSAM_DEVICE void t2i_block(const Smem& s, int rank, int nt, int nr, const float* __restrict__ q_w, const float* __restrict__ q_b,
+                             const float* __restrict__ o_w, const float* __restrict__ o_b, const float* __restrict__ n_w,
+                             const float* __restrict__ n_b, const __nv_bfloat16* __restrict__ kv, int ldkv, int ns, int warp,
+                             int lane) {
+  // q slice: columns [32 rank, 32 rank + 32), scaled by 1/sqrt(16)
+  for (int rb = 0; rb < nr; rb += 8)
+    gemv8<E>(s.Bqp + rb * E, E, q_w + static_cast<size_t>(32 * rank) * E, E, 32, warp, lane,
+          [&](int r, int c, float v) { s.Lq[(rb + r) * 64 + c] = (v + __ldg(q_b + 32 * rank + c)) * 0.25f; });
+  __syncthreads();
+  if (nr <= 16) t2i_attention<1>(s, rank, nt, nr, kv, ldkv, ns, warp, lane);   // one or two 16-token tiles
+  else t2i_attention<2>(s, rank, nt, nr, kv, ldkv, ns, warp, lane);
   cluster_sync();
   // out_proj (K = 128) + residual: columns [64 rank, 64 rank + 64) -> By of every CTA
   for (int rb = 0; rb < nr; rb += 8)
-    gemv8(s.Ba + rb * E, E, 128, o_w + static_cast<size_t>(64 * rank) * 128, 128, 64, warp, lane, [&](int r, int c, float v) {
+    gemv8<128>(s.Ba + rb * E, E, o_w + static_cast<size_t>(64 * rank) * 128, 128, 64, warp, lane, [&](int r, int c, float v) {
       const int row = rb + r, n = 64 * rank + c;
       bcast(s, s.By + row * E + n, v + __ldg(o_b + n) + s.Bq[row * E + n]);
     });
@@ -281,8 +368,8 @@ ULLSAM_DEVICE Smem carve(float* base, int nr) {
   s.Lk = s.Lq + nr * 64;
   s.Lv = s.Lk + nr * 64;
   s.hid = s.Lv + nr * 64;
-  s.qs = s.hid + nr * 512;
-  s.red = s.qs + 2 * T2I_TG * 16;
+  s.red = s.hid + nr * 512;
+  s.stage = s.red + FIXED_FLOATS;   // ns buffers of T2I_STAGE_FLOATS (16-byte aligned: every term above is a multiple of 4 floats)
   return s;
 }
 
@@ -319,7 +406,7 @@ ULLSAM_DEVICE void store_queries(const Smem& s, float* __restrict__ queries, int
 // ---------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FT, 1)
 dec_token_layer_kernel(DecTokLayer L, float* __restrict__ queries, const float* __restrict__ tokens,
-                       const __nv_bfloat16* __restrict__ proj, int ldkv, int nt, int nr, float* __restrict__ k128,
+                       const __nv_bfloat16* __restrict__ proj, int ldkv, int nt, int nr, int ns, float* __restrict__ k128,
                        float* __restrict__ v128) {
   extern __shared__ __align__(16) float smem_f[];
   const Smem s = carve(smem_f, nr);
@@ -332,11 +419,11 @@ dec_token_layer_kernel(DecTokLayer L, float* __restrict__ queries, const float* 
   // ---- self attention (transformer.py:156-163): heads 2 rank, 2 rank + 1 = columns [64 rank, 64 rank + 64) ----
   const int n0 = 64 * rank;
   for (int rb = 0; rb < nr; rb += 8) {
-    gemv8(s.Bqp + rb * E, E, E, L.sq_w + static_cast<size_t>(n0) * E, E, 64, warp, lane,
+    gemv8<E>(s.Bqp + rb * E, E, L.sq_w + static_cast<size_t>(n0) * E, E, 64, warp, lane,
           [&](int rr, int c, float v) { s.Lq[(rb + rr) * 64 + c] = (v + __ldg(L.sq_b + n0 + c)) * 0.17677669529663687f; });  // 1/sqrt(32)
-    gemv8(s.Bqp + rb * E, E, E, L.sk_w + static_cast<size_t>(n0) * E, E, 64, warp, lane,
+    gemv8<E>(s.Bqp + rb * E, E, L.sk_w + static_cast<size_t>(n0) * E, E, 64, warp, lane,
           [&](int rr, int c, float v) { s.Lk[(rb + rr) * 64 + c] = v + __ldg(L.sk_b + n0 + c); });
-    gemv8(s.Bq + rb * E, E, E, L.sv_w + static_cast<size_t>(n0) * E, E, 64, warp, lane,
+    gemv8<E>(s.Bq + rb * E, E, L.sv_w + static_cast<size_t>(n0) * E, E, 64, warp, lane,
           [&](int rr, int c, float v) { s.Lv[(rb + rr) * 64 + c] = v + __ldg(L.sv_b + n0 + c); });
   }
   __syncthreads();
@@ -362,7 +449,7 @@ dec_token_layer_kernel(DecTokLayer L, float* __restrict__ queries, const float* 
   DT_STAMP("self attn");
   // out_proj (+ residual unless this is the first layer: there the attention output REPLACES the queries, :157-158)
   for (int rb = 0; rb < nr; rb += 8)
-    gemv8(s.Ba + rb * E, E, E, L.so_w + static_cast<size_t>(n0) * E, E, 64, warp, lane, [&](int rr, int c, float v) {
+    gemv8<E>(s.Ba + rb * E, E, L.so_w + static_cast<size_t>(n0) * E, E, 64, warp, lane, [&](int rr, int c, float v) {
       const int row = rb + rr, n = n0 + c;
       bcast(s, s.By + row * E + n, v + __ldg(L.so_b + n) + (L.skip_pe ? 0.f : s.Bq[row * E + n]));
     });
@@ -373,19 +460,19 @@ dec_token_layer_kernel(DecTokLayer L, float* __restrict__ queries, const float* 
   DT_STAMP("norm1");
 
   // ---- tokens attend to the image, norm2 (:165-170) ----
-  t2i_block(s, rank, nt, nr, L.tq_w, L.tq_b, L.to_w, L.to_b, L.n2_w, L.n2_b, proj + static_cast<size_t>(r) * 4096 * ldkv, ldkv, warp,
+  t2i_block(s, rank, nt, nr, L.tq_w, L.tq_b, L.to_w, L.to_b, L.n2_w, L.n2_b, proj + static_cast<size_t>(r) * 4096 * ldkv, ldkv, ns, warp,
             lane);
 
   DT_STAMP("t2i block");
   // ---- MLP (:172-175): this CTA's quarter of the hidden units, then its partial of lin2 over that quarter ----
   const int hq = L.mlp_dim / CL;   // 512
   for (int rb = 0; rb < nr; rb += 8)
-    gemv8(s.Bq + rb * E, E, E, L.m1_w + static_cast<size_t>(hq * rank) * E, E, hq, warp, lane,
+    gemv8<E>(s.Bq + rb * E, E, L.m1_w + static_cast<size_t>(hq * rank) * E, E, hq, warp, lane,
           [&](int rr, int c, float v) { s.hid[(rb + rr) * 512 + c] = fmaxf(v + __ldg(L.m1_b + hq * rank + c), 0.f); });
   __syncthreads();
   DT_STAMP("mlp lin1");
   for (int rb = 0; rb < nr; rb += 8)
-    gemv8(s.hid + rb * 512, 512, hq, L.m2_w + hq * rank, L.mlp_dim, E, warp, lane,
+    gemv8<512>(s.hid + rb * 512, 512, L.m2_w + hq * rank, L.mlp_dim, E, warp, lane,
           [&](int rr, int c, float v) { s.part[(rb + rr) * E + c] = v; });
   cluster_sync();
   DT_STAMP("mlp lin2");
@@ -405,14 +492,15 @@ dec_token_layer_kernel(DecTokLayer L, float* __restrict__ queries, const float* 
 
   // ---- k / v of the tokens for the image->token attention (:177-180): 128 columns, 32 per CTA ----
   for (int rb = 0; rb < nr; rb += 8) {
-    gemv8(s.Bqp + rb * E, E, E, L.ik_w + static_cast<size_t>(32 * rank) * E, E, 32, warp, lane, [&](int rr, int c, float v) {
+    gemv8<E>(s.Bqp + rb * E, E, L.ik_w + static_cast<size_t>(32 * rank) * E, E, 32, warp, lane, [&](int rr, int c, float v) {
       if (rb + rr < nt) k128[(static_cast<size_t>(r) * nt + rb + rr) * 128 + 32 * rank + c] = v + __ldg(L.ik_b + 32 * rank + c);
     });
-    gemv8(s.Bq + rb * E, E, E, L.iv_w + static_cast<size_t>(32 * rank) * E, E, 32, warp, lane, [&](int rr, int c, float v) {
+    gemv8<E>(s.Bq + rb * E, E, L.iv_w + static_cast<size_t>(32 * rank) * E, E, 32, warp, lane, [&](int rr, int c, float v) {
       if (rb + rr < nt) v128[(static_cast<size_t>(r) * nt + rb + rr) * 128 + 32 * rank + c] = v + __ldg(L.iv_b + 32 * rank + c);
     });
   }
   DT_STAMP("i2t k/v");
+  DT_END;
   if (rank == 0) store_queries(s, queries, r, nt);
 }
 
@@ -423,14 +511,14 @@ dec_token_layer_kernel(DecTokLayer L, float* __restrict__ queries, const float* 
 // ---------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(FT, 1)
 dec_token_final_kernel(DecTokFinal F, float* __restrict__ queries, const float* __restrict__ tokens,
-                       const __nv_bfloat16* __restrict__ proj, int ldkv, int nt, int nr, float* __restrict__ hyper,
+                       const __nv_bfloat16* __restrict__ proj, int ldkv, int nt, int nr, int ns, float* __restrict__ hyper,
                        float* __restrict__ iou4) {
   extern __shared__ __align__(16) float smem_f[];
   const Smem s = carve(smem_f, nr);
   const int rank = static_cast<int>(cluster_ctarank()), r = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   load_tokens(s, queries, tokens, r, nt, nr, true);
-  t2i_block(s, rank, nt, nr, F.tq_w, F.tq_b, F.to_w, F.to_b, F.nf_w, F.nf_b, proj + static_cast<size_t>(r) * 4096 * ldkv, ldkv, warp,
+  t2i_block(s, rank, nt, nr, F.tq_w, F.tq_b, F.to_w, F.to_b, F.nf_w, F.nf_b, proj + static_cast<size_t>(r) * 4096 * ldkv, ldkv, ns, warp,
             lane);
   if (rank == 0) store_queries(s, queries, r, nt);
   if (hyper == nullptr) return;
@@ -471,7 +559,10 @@ dec_token_final_kernel(DecTokFinal F, float* __restrict__ queries, const float* 
   }
 }
 
-size_t fused_smem_bytes(int nr) { return (static_cast<size_t>(nr) * ROW_FLOATS + FIXED_FLOATS) * sizeof(float); }
+int fused_stages(int nr) { return nr <= 8 ? 6 : (nr <= 16 ? 4 : 2); }   // cp.async ring depth of the token->image attention
+size_t fused_smem_bytes(int nr) {
+  return (static_cast<size_t>(nr) * ROW_FLOATS + FIXED_FLOATS + fused_stages(nr) * T2I_STAGE_FLOATS) * sizeof(float);
+}
 
 const char* check_launch() {
   cudaError_t e = cudaGetLastError();
@@ -491,7 +582,7 @@ const char* launch_dec_token_layer(const DecTokLayer& L, float* queries, const f
   const size_t smem = fused_smem_bytes(nr);
   static PerDeviceOnce configured;
   if (const char* e = set_max_smem_once(configured, dec_token_layer_kernel, static_cast<int>(fused_smem_bytes(kDecFusedMaxTokens)))) return e;
-  dec_token_layer_kernel<<<dim3(CL, R), FT, smem, stream>>>(L, queries, tokens, proj, ldkv, Nt, nr, k128, v128);
+  dec_token_layer_kernel<<<dim3(CL, R), FT, smem, stream>>>(L, queries, tokens, proj, ldkv, Nt, nr, fused_stages(nr), k128, v128);
   return check_launch();
 }
 
@@ -502,7 +593,7 @@ const char* launch_dec_token_final(const DecTokFinal& F, float* queries, const f
   const size_t smem = fused_smem_bytes(nr);
   static PerDeviceOnce configured;
   if (const char* e = set_max_smem_once(configured, dec_token_final_kernel, static_cast<int>(fused_smem_bytes(kDecFusedMaxTokens)))) return e;
-  dec_token_final_kernel<<<dim3(CL, R), FT, smem, stream>>>(F, queries, tokens, proj, ldkv, Nt, nr, hyper, iou4);
+  dec_token_final_kernel<<<dim3(CL, R), FT, smem, stream>>>(F, queries, tokens, proj, ldkv, Nt, nr, fused_stages(nr), hyper, iou4);
   return check_launch();
 }
 

@@ -32,7 +32,9 @@ constexpr int GEMM_EPI_WARP0 = 4;
 #endif
 // bit (j & 3) set: element j of a chunk takes the 16th power of the GELU's erf by RCP + squarings instead of LG2/EX2
 #ifndef ULLSAM_GELU_RCP_MASK
-#define ULLSAM_GELU_RCP_MASK 0x1  // measured on lin1: 0x0 512 us, 0x1 503, 0x5 506, 0xF 519
+#define ULLSAM_GELU_RCP_MASK 0x1  // measured on lin1: 0x0 512 us, 0x1 503, 0x5 506, 0xF 519.  (Round 2: a MUFU-free degree-7
+                                  // polynomial form on 1/4, 1/2, 3/4 or all of the elements: 489, 494, 502, 501 us against 490 —
+                                  // the epilogue is bound by its instruction count, not by the special-function unit.)
 #endif
 #ifndef ULLSAM_GEMM_EARLY_RELEASE
 #define ULLSAM_GEMM_EARLY_RELEASE 1
