@@ -136,6 +136,41 @@ def test_gemm_qkv_window_partition_on_store():
     assert (q.float()[(~valid).expand_as(q)] == 7.0).all(), "q rows of padding tokens must stay untouched"
 
 
+@pytest.mark.parametrize("M,act", [(2 * 4096, 0), (4096 + 77, 2)])
+def test_gemm_bf16_with_position_addend(M, act):
+    """The decoder's image-side projections (transformer.py:166-167, 178-179): (keys + key_pe) W^T + b is computed as
+    keys W^T + b + (key_pe W^T), the second term being one fp32 [4096, N] table shared by all prompts, added in the epilogue
+    (after the transpose, with coalesced loads) before the single rounding to bf16."""
+    from ullsam_b200 import _lib, ops
+
+    a, w, b = _mk(M, 384, 256, 6)
+    pos = torch.randn(4096, 384, device="cuda") * 0.3
+    out = ops.gemm(a, w, b, epi=_lib.EPI_BF16, act=act, pos=pos)
+    ref = _ref(a, w, b) + pos.repeat((M + 4095) // 4096, 1)[:M]
+    if act == 2:
+        ref = torch.relu(ref)
+    _close(out, ref, 8e-3, f"bf16 + pos, M={M} act={act}")
+
+
+@pytest.mark.parametrize("M", [1024, 4096 + 50])
+def test_gemm_residual_layernorm_256(M):
+    """TwoWayAttentionBlock's image side: keys = norm4(keys + out_proj(attn)) (transformer.py:178-182), in place on the
+    fp32 keys with a bf16 copy for the next GEMM."""
+    from ullsam_b200 import _lib, ops
+
+    a, w, b = _mk(M, 256, 128, 7)
+    g = torch.Generator(device="cuda").manual_seed(8)
+    keys = torch.randn(M, 256, device="cuda", generator=g)
+    ln_w = torch.randn(256, device="cuda", generator=g) * 0.1 + 1
+    ln_b = torch.randn(256, device="cuda", generator=g) * 0.1
+    ref = torch.nn.functional.layer_norm(_ref(a, w, b) + keys, (256,), ln_w, ln_b, 1e-5)
+    x = keys.clone()
+    out2 = torch.empty(M, 256, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, w, b, epi=_lib.EPI_LN_RES, out=x, residual=x, ln_w=ln_w, ln_b=ln_b, ln_eps=1e-5, out2=out2)   # in place
+    _close(x, ref, 2e-3, f"LN(res + gemm) fp32, M={M}")
+    _close(out2, ref, 8e-3, f"LN(res + gemm) bf16 copy, M={M}")
+
+
 def _ln2d(x, w, b, eps):
     u = x.mean(-1, keepdim=True)
     s = (x - u).pow(2).mean(-1, keepdim=True)
