@@ -255,15 +255,17 @@ def _ln(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
 
 
 def transformer_forward(sd: SD, image_embedding: torch.Tensor, image_pe: torch.Tensor, point_embedding: torch.Tensor,
-                        cfg: SamConfig, prefix: str = "mask_decoder.transformer.") -> Tuple[torch.Tensor, torch.Tensor]:
-    """TwoWayTransformer.forward, transformer.py:62-108 (blocks: :153-184)."""
+                        cfg: SamConfig, prefix: str = "mask_decoder.transformer.",
+                        skip_first_layer_pe: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """TwoWayTransformer.forward, transformer.py:62-108 (blocks: :153-184).  ``skip_first_layer_pe`` is the constructor flag of
+    TwoWayAttentionBlock (:134, set to ``i == 0`` at :52); False is only used by the tests as a negative control."""
     keys = image_embedding.flatten(2).permute(0, 2, 1)
     key_pe = image_pe.flatten(2).permute(0, 2, 1)
     queries = point_embedding
     H = cfg.dec_heads
     for i in range(cfg.dec_depth):
         p = f"{prefix}layers.{i}."
-        if i == 0:  # skip_first_layer_pe: the output REPLACES the queries (:157-158)
+        if i == 0 and skip_first_layer_pe:  # the output REPLACES the queries (:157-158)
             queries = _dec_attention(sd, p + "self_attn.", queries, queries, queries, H)
         else:
             qq = queries + point_embedding
