@@ -156,7 +156,13 @@ const char* ullsam_profile_category_name(int i);
 typedef struct {
   int32_t epi;  /* 0 bf16 | 1 +residual fp32 | 2 qkv split | 3 +pos fp32 | 4 LN2d bf16 | 5 LN2d NCHW | 6 fp32 |
                  * 11 +residual fp32 AND the following nn.LayerNorm -> out2 bf16 (Block.norm2 / next Block.norm1,
-                 *    image_encoder.py:166-182), optionally window-partitioned (image_encoder.py:243-264) */
+                 *    image_encoder.py:166-182), optionally window-partitioned (image_encoder.py:243-264)
+                 * LayerNorm folded into the GEMMs around it (the default encoder path; Block.norm1 / norm2, image_encoder.py:166-182):
+                 *    LN(x) W^T + b = rstd * (x (gamma*W)^T - mean * s) + c,  s_n = sum_k (gamma*W)_nk,  c_n = sum_k beta_k W_nk + b_n
+                 * 12 epi 1, plus out2 = bf16(out) and row_stats[row][2 * (n / 256) + (n % 256) / 128] = (sum, sum of squares)
+                 *    of the row's 128-column slice | 13 epi 3 with the same two extra outputs
+                 * 14 epi 2 on the un-normalised rows: W = bf16(gamma*W), bias = c, fold_s = s, mean / rstd from row_stats
+                 *    (K / 128 slices), pad_bias = b | 15 epi 0 + GELU(erf), same */
   int32_t M, N, K;
   int32_t a_conv3, conv_c;
   const void* A;     /* bf16 */
@@ -182,6 +188,9 @@ typedef struct {
                          *        (image_encoder.py:243-264) into q/k/v [B*25][heads][196][64] and also writes the k / v rows
                          *        of the 804 padding tokens per image (= bias: they are zero after norm1, :168-172, and
                          *        are attended to); their q rows are left untouched (cropped by window_unpartition) */
+  float* row_stats;      /* epi 12, 13 (written), 14, 15 (read): fp32 [M][8][2] */
+  const float* fold_s;   /* epi 14, 15: [N] */
+  const float* pad_bias; /* epi 14 with ln_partition: [N] */
 } ullsam_gemm_desc;
 int ullsam_op_gemm(const ullsam_gemm_desc* d, void* stream);
 

@@ -136,6 +136,128 @@ def test_gemm_qkv_window_partition_on_store():
     assert (q.float()[(~valid).expand_as(q)] == 7.0).all(), "q rows of padding tokens must stay untouched"
 
 
+# ---- LayerNorm folded into the GEMMs on either side of it (the encoder's default path; Block.norm1 / norm2,
+# image_encoder.py:166-182):  LN(x) W^T + b = rstd * (x (gamma*W)^T - mean * s) + c ----
+
+def _row_stats(x):
+    """[M, D] fp32 -> the producer epilogues' statistics buffer [M, 8, 2]: (sum, sum of squares) per 128-column slice."""
+    from ullsam_b200 import _lib
+    M, D = x.shape
+    st = torch.zeros(M, _lib.STAT_SLOTS, 2, device=x.device)
+    xs = x.reshape(M, D // 128, 128)
+    st[:, : D // 128, 0] = xs.sum(-1)
+    st[:, : D // 128, 1] = (xs * xs).sum(-1)
+    return st
+
+
+@pytest.mark.parametrize("M,N,K,patch", [(4096, 768, 768, False), (2 * 4096 + 300, 1024, 4096, False), (300, 768, 768, False),
+                                         (4096, 768, 768, True)])
+def test_gemm_residual_with_row_statistics(M, N, K, patch):
+    """EPI_RES_STATS / EPI_PATCH_STATS: the fp32 result is the plain epilogue's, out2 is its bf16 copy and row_stats holds
+    the partial sums of every 128-column slice (computed from the fp32 values)."""
+    from ullsam_b200 import _lib, ops
+
+    a, w, b = _mk(M, N, K, 11)
+    st = torch.full((M, _lib.STAT_SLOTS, 2), -7.0, device="cuda")
+    xb = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    if patch:
+        pos = torch.randn(4096, N, device="cuda")
+        ref = _ref(a, w, b) + pos.repeat(M // 4096, 1)
+        x = ops.gemm(a, w, b, epi=_lib.EPI_PATCH_STATS, pos=pos, out2=xb, row_stats=st)
+        plain = ops.gemm(a, w, b, epi=_lib.EPI_PATCH, pos=pos)
+    else:
+        res = torch.randn(M, N, device="cuda") * 2 + 0.3
+        ref = _ref(a, w, b) + res
+        x = res.clone()
+        ops.gemm(a, w, b, epi=_lib.EPI_RES_STATS, out=x, residual=x, out2=xb, row_stats=st)
+        plain = res.clone()
+        ops.gemm(a, w, b, epi=_lib.EPI_RES_F32, out=plain, residual=plain)
+    torch.cuda.synchronize()
+    _close(x, ref, 1e-4, "res_stats out")
+    assert torch.equal(x, plain), "the statistics epilogue must not change the fp32 result"
+    assert torch.equal(xb, x.bfloat16()), "out2 is the bf16 rounding of out"
+    want = _row_stats(x)
+    ns = N // 128
+    _close(st[:, :ns, 0], want[:, :ns, 0], 1e-5, "row sums")
+    _close(st[:, :ns, 1], want[:, :ns, 1], 1e-5, "row sums of squares")
+    assert (st[:, ns:] == -7.0).all(), "slots beyond N / 128 are not written"
+
+
+def _fold_case(M, N, D, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    # a residual-stream-like input: per-channel scales, a few large channels, a non-zero row mean
+    x = torch.randn(M, D, device="cuda", generator=g) * (0.5 + torch.rand(D, device="cuda", generator=g)) + 0.2
+    x[:, 5] *= 20.0
+    x[:, D - 3] += 8.0
+    gamma = 1.0 + 0.3 * torch.randn(D, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(D, device="cuda", generator=g)
+    w = torch.randn(N, D, device="cuda", generator=g) * 0.05
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    ref = torch.nn.functional.layer_norm(x, (D,), gamma, beta, 1e-6) @ w.t() + b
+    wf = (gamma * w).bfloat16()
+    _fold_case.affine = (gamma, beta)
+    return x, w, b, ref, wf, wf.float().sum(1).contiguous(), (w @ beta + b).contiguous()
+
+
+@pytest.mark.parametrize("M,D", [(4096, 768), (4096 + 200, 1024), (200, 768)])
+def test_gemm_gelu_with_folded_layernorm(M, D):
+    """EPI_GELU_FOLD = GELU(LayerNorm(x) W^T + b) computed from the bf16 copy of x, gamma*W and the row statistics;
+    compared with fp32 torch and with the unfolded CUDA path (LayerNorm kernel -> GEMM) it replaces."""
+    from ullsam_b200 import _lib, ops
+
+    N = 3072
+    x, w, b, ref, wf, s, c = _fold_case(M, N, D, 21)
+    out = ops.gemm(x.bfloat16(), wf, c, epi=_lib.EPI_GELU_FOLD, fold_s=s, row_stats=_row_stats(x), ln_eps=1e-6)
+    torch.cuda.synchronize()
+    gref = torch.nn.functional.gelu(ref)
+    _close(out, gref, 1.2e-2, f"gelu_fold M={M} D={D}")
+    e_fold = ((out.float() - gref).norm() / gref.norm()).item()
+    print(f"gelu_fold rel-L2 vs fp32: {e_fold:.3e}")
+    assert e_fold <= 6e-3
+    if M % 4096 == 0:  # the path it replaces: LayerNorm kernel (fp32 -> bf16), then the plain GELU GEMM
+        gamma, beta = _fold_case.affine
+        xn = ops.layernorm(x.reshape(M // 4096, 64, 64, D).contiguous(), gamma, beta, 1e-6).reshape(M, D)
+        plain = ops.gemm(xn, w.bfloat16(), b, epi=_lib.EPI_BF16, act=_lib.ACT_GELU)
+        e_plain = ((plain.float() - gref).norm() / gref.norm()).item()
+        print(f"          unfolded path vs fp32: {e_plain:.3e}")
+        assert e_fold <= 1.5 * e_plain + 1e-3
+
+
+@pytest.mark.parametrize("partition", [False, True])
+def test_gemm_qkv_with_folded_layernorm(partition):
+    """EPI_QKV_FOLD: head split (and window_partition on the store) of LayerNorm(x) W^T + b; the k / v rows of the
+    window-padding tokens are the projection's own bias b (they are zero AFTER the norm, image_encoder.py:168-172)."""
+    from ullsam_b200 import _lib, ops
+
+    B, heads, D = 2, 12, 768
+    M, N = B * 4096, 3 * D
+    x, w, b, ref, wf, s, c = _fold_case(M, N, D, 22)
+    if partition:
+        q = torch.full((B * 25, heads, 196, 64), 7.0, dtype=torch.bfloat16, device="cuda")
+        k, v = q.clone(), q.clone()
+        ops.gemm(x.bfloat16(), wf, c, epi=_lib.EPI_QKV_FOLD, qkv=(q, k, v), T=196, heads=heads, ln_partition=True, fold_s=s,
+                 pad_bias=b, row_stats=_row_stats(x), ln_eps=1e-6)
+        y = ref.reshape(B, 64, 64, N)
+        yp = b.expand(B, 70, 70, N).clone()
+        yp[:, :64, :64] = y
+        r = yp.reshape(B, 5, 14, 5, 14, 3, heads, 64).permute(5, 0, 1, 3, 6, 2, 4, 7).reshape(3, B * 25, heads, 196, 64)
+        valid = torch.nn.functional.pad(torch.ones(B, 64, 64, device="cuda"), (0, 6, 0, 6))
+        valid = valid.reshape(B, 5, 14, 5, 14).permute(0, 1, 3, 2, 4).reshape(B * 25, 1, 196, 1).bool()
+        _close(k, r[1], 1.2e-2, "folded windowed k")
+        _close(v, r[2], 1.2e-2, "folded windowed v")
+        _close(torch.where(valid, q.float(), r[0]), r[0], 1.2e-2, "folded windowed q (real tokens)")
+        assert (q.float()[(~valid).expand_as(q)] == 7.0).all()
+    else:
+        T, G = 4096, B
+        q = torch.zeros(G, heads, T, 64, dtype=torch.bfloat16, device="cuda")
+        k, v = torch.zeros_like(q), torch.zeros_like(q)
+        ops.gemm(x.bfloat16(), wf, c, epi=_lib.EPI_QKV_FOLD, qkv=(q, k, v), T=T, heads=heads, fold_s=s, row_stats=_row_stats(x),
+                 ln_eps=1e-6)
+        r = ref.reshape(G, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+        for name, got, rr in (("q", q, r[0]), ("k", k, r[1]), ("v", v, r[2])):
+            _close(got, rr, 1.2e-2, f"folded qkv[{name}]")
+
+
 @pytest.mark.parametrize("M,act", [(2 * 4096, 0), (4096 + 77, 2)])
 def test_gemm_bf16_with_position_addend(M, act):
     """The decoder's image-side projections (transformer.py:166-167, 178-179): (keys + key_pe) W^T + b is computed as

@@ -173,6 +173,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* o_done = p_ready + QT;      // [QT][2]: PV(j) of query tile qt commits to o_done[qt*2 + (j & 1)]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2 * QT);
 
+  pdl_wait();      // (the first TMA loads below already read q / k / v)
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gh = blockIdx.y;                       // group * heads + head
   const int qblock = blockIdx.x;                   // block of QT*128 queries inside the group
@@ -641,6 +643,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         TL_STAMP(3);
         tmem_wait_st();
+        // Back-pressure on the hand-over: P(j) must not be announced before the MMA warp has OBSERVED P(j-1) of this query
+        // tile.  Nothing else enforces that: S(j+1) of this query tile goes out with the PV of the OTHER query tile's previous
+        // item (S(n+3) is issued in iteration n), i.e. before the MMA warp looks at p_ready for P(j-1), and that warp waits
+        // for its K / V operands first.  If a K tile arrives later than one softmax tile takes (~1.5 us), this warp announces
+        // P(j-1) and P(j) back to back, p_ready[qt] is two phases ahead of the parity the MMA warp then waits for, and that
+        // wait never returns.  Seen once, in bench.py's end-to-end loop (host-to-device copies competing for HBM): qt 1 had
+        // announced P(1) and P(3) while the MMA warp was still waiting for K tile 2 (watchdog dump:
+        // profiles/r2_attention_handover_race.txt).  PV(j-1) is committed by the iteration that observed P(j-1), so its
+        // o_done phase is the proof; in the normal case it retired long ago (one successful try_wait).  The parity is
+        // unambiguous for the same reason as in the rescale above: having seen S(j), PV(j-2) of this query tile has
+        // retired, and PV(j+1) cannot exist before this warp announces P(j+1).
+        if (j > 0) mbar_wait(&o_done[qt * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[qt]);
@@ -875,7 +889,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_st4(s_addr + hs * 28 + 24, *reinterpret_cast<uint32_t(*)[4]>(&v[0][24]));
       }
       tmem_wait_st();
-      if (j > 1) mbar_wait(&o_done[qt * 2 + (j & 1)], ((j - 2) >> 1) & 1);  // PV(j-2): long retired
+      // (hand-over back-pressure, see the one-thread-per-row path: P(j) is not announced before the MMA warp has observed
+      //  P(j-1); waiting for PV(j-2) only, as this path did, still lets p_ready run two phases ahead)
+      if (j > 0) mbar_wait(&o_done[qt * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[qt]);
@@ -928,6 +944,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // k: bf16 [GH][T][64].  One CTA per (group, head); 128 bytes per row, 16-byte loads.
 __global__ void __launch_bounds__(256) k_norm_max_kernel(const __nv_bfloat16* __restrict__ k, int T, float* __restrict__ out) {
   __shared__ float red[8];
+  pdl_wait();
+  pdl_trigger();
   const uint4* base = reinterpret_cast<const uint4*>(k + static_cast<size_t>(blockIdx.x) * T * 64);
   float mx = 0.f;
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
@@ -971,8 +989,7 @@ const char* launch_t(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
   auto kern = attention_kernel<GRID>;
   if ((e = set_max_smem_once(configured, kern, A::TOTAL))) return e;
   dim3 grid((A::T + A::NROWS - 1) / A::NROWS, G * heads);
-  kern<<<grid, A::THREADS, A::TOTAL, stream>>>(tq, tk, tv, trh, trw, heads, kmax, out);
-  cudaError_t ce = cudaGetLastError();
+  cudaError_t ce = launch_pdl(kern, grid, dim3(A::THREADS), A::TOTAL, stream, 1, tq, tk, tv, trh, trw, heads, kmax, out);
   return ce == cudaSuccess ? nullptr : cudaGetErrorString(ce);
 }
 
@@ -988,7 +1005,8 @@ const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, con
     float* kmax = kmax_scratch;
     if (kmax == nullptr && cudaMallocAsync(&kmax, static_cast<size_t>(G) * heads * sizeof(float), stream) != cudaSuccess)
       return "attention: cudaMallocAsync failed";
-    k_norm_max_kernel<<<G * heads, 256, 0, stream>>>(k, 4096, kmax);
+    if (launch_pdl(k_norm_max_kernel, dim3(G * heads), dim3(256), 0, stream, 1, k, 4096, kmax) != cudaSuccess)
+      return "attention: key-norm pre-pass launch failed";
     const char* e = launch_t<64>(q, k, v, rel_h, rel_w, G, heads, kmax, out, stream);
     if (kmax_scratch == nullptr) cudaFreeAsync(kmax, stream);
     return e;

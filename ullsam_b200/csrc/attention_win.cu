@@ -93,6 +93,8 @@ windowed_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   uint64_t* tab_done = epi_done + 2;    // [qt]: this query tile's bias-table MMAs have retired (its softmax warps may gather)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tab_done + 2);
 
+  pdl_wait();      // (the loads issued before the CTA-wide sync already read q / k / v)
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Persistent CTA: items (window * heads + head) blockIdx.x, blockIdx.x + gridDim.x, ...  Every mbarrier completes exactly
   // one phase per item, so the wait parity of item number `it` is simply it & 1 and nothing is ever re-initialised.
@@ -434,8 +436,8 @@ const char* launch_attention_windowed_v2(const __nv_bfloat16* q, const __nv_bflo
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = nitems < 2 * sms ? nitems : 2 * sms;   // two resident CTAs per SM, each walks items grid apart
-  windowed_attention_kernel<<<grid, W::THREADS, W::TOTAL, stream>>>(tq, tq1, tk, tv, trh, trw, heads, nitems, out);
-  cudaError_t ce = cudaGetLastError();
+  cudaError_t ce = launch_pdl(windowed_attention_kernel, dim3(grid), dim3(W::THREADS), W::TOTAL, stream, 1, tq, tq1, tk, tv, trh, trw,
+                              heads, nitems, out);
   return ce == cudaSuccess ? nullptr : cudaGetErrorString(ce);
 }
 

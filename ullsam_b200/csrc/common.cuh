@@ -112,6 +112,9 @@ ULLSAM_DEVICE bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+#ifndef ULLSAM_MBAR_TIMEOUT_NS   // (compute-sanitizer builds raise it: instrumented kernels run 10-100x slower, tools/build_sanitizer_lib.sh)
+#define ULLSAM_MBAR_TIMEOUT_NS 4000000000ull
+#endif
 // Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) after ~4 s of wall time instead of a hung
 // GPU.  The clock is only read once the wait has already failed 256 times, so the normal path costs nothing.
 ULLSAM_DEVICE uint64_t global_timer_ns() {
@@ -127,7 +130,7 @@ ULLSAM_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++spins & 255u) == 0) {
       const uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
-      if (now - t0 > 4000000000ull) {
+      if (now - t0 > ULLSAM_MBAR_TIMEOUT_NS) {
         printf("ullsam: mbarrier timeout block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y, threadIdx.x,
                smem_u32(bar), parity);
         __trap();
@@ -135,6 +138,13 @@ ULLSAM_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+
+// Programmatic dependent launch (kernels launched with launch_pdl(), host_util.h): the grid may be scheduled while its
+// predecessor in the stream is still draining; pdl_wait() returns once the predecessor has completed and its memory is
+// visible — every thread calls it before its first access to global memory.  pdl_trigger() lets the NEXT grid be scheduled
+// as soon as every CTA of this one has got this far.  Both are no-ops for ordinary launches.
+ULLSAM_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+ULLSAM_DEVICE void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // generic-proxy writes (st.shared) -> async proxy (UMMA / TMA) visibility
 ULLSAM_DEVICE void fence_proxy_async_smem() {

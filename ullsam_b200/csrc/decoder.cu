@@ -242,6 +242,8 @@ __global__ void __launch_bounds__(256) t2i_attention_kernel(const float* __restr
 __global__ void __launch_bounds__(256) i2t_attention_kernel(const __nv_bfloat16* __restrict__ proj, int ldp, int q_col,
                                                             const float* __restrict__ k, const float* __restrict__ v,
                                                             int Nt, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   // k, v in shared memory as [Nt][8 heads][20]: the 16 floats of a head padded to 20, so that the eight heads of a
   // token (the 8 threads of one 128-bit load phase) hit eight different 16-byte bank groups
   extern __shared__ __align__(16) float kvs[];
@@ -310,6 +312,8 @@ __global__ void __launch_bounds__(256) i2t_attention_kernel(const __nv_bfloat16*
 __global__ void __launch_bounds__(256) keys_init_kernel(const float* __restrict__ emb, int P, const float* __restrict__ dense,
                                                         int dense_mode, int dense_batch, float* __restrict__ keys_f32,
                                                         __nv_bfloat16* __restrict__ keys_bf16) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[32][33];
   const int r = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -341,6 +345,8 @@ __global__ void __launch_bounds__(256) keys_init_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) tok_init_kernel(const float* __restrict__ iou_token, const float* __restrict__ mask_tokens,
                                                        int nm, const float* __restrict__ sparse, int Ns,
                                                        float* __restrict__ tokens) {
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x, Nt = 1 + nm + Ns;
   for (int idx = threadIdx.x; idx < Nt * 256; idx += 256) {
     const int t = idx >> 8, c = idx & 255;
@@ -355,6 +361,8 @@ __global__ void __launch_bounds__(256) tok_init_kernel(const float* __restrict__
 // out[r][j][...] = in[r][m0 + j][...]: channel slice of [R][4][inner] tensors (mask_decoder.py:102-107)
 __global__ void __launch_bounds__(256) slice_copy_kernel(const float* __restrict__ in, int C, int m0, int cnt, size_t inner,
                                                          float* __restrict__ out, size_t total) {
+  pdl_wait();
+  pdl_trigger();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t in_i = i % inner;
@@ -405,19 +413,19 @@ const char* launch_i2t_attention(const __nv_bfloat16* proj, int ldp, int q_col, 
     static PerDeviceOnce configured;
     if (const char* ce = set_max_smem_once(configured, i2t_attention_kernel, 64 * 320 * 4)) return ce;
   }
-  i2t_attention_kernel<<<dim3(128, R), 256, Nt * 320 * sizeof(float), stream>>>(proj, ldp, q_col, k, v, Nt, out);
+  launch_pdl(i2t_attention_kernel, dim3(128, R), dim3(256), Nt * 320 * sizeof(float), stream, 1, proj, ldp, q_col, k, v, Nt, out);
   return last_err();
 }
 
 const char* launch_keys_init(const float* emb, int R, int P, const float* dense, int dense_mode, int dense_batch,
                              float* keys_f32, __nv_bfloat16* keys_bf16, cudaStream_t stream) {
-  keys_init_kernel<<<dim3(128, 8, R), 256, 0, stream>>>(emb, P, dense, dense_mode, dense_batch, keys_f32, keys_bf16);
+  launch_pdl(keys_init_kernel, dim3(128, 8, R), dim3(256), 0, stream, 1, emb, P, dense, dense_mode, dense_batch, keys_f32, keys_bf16);
   return last_err();
 }
 
 const char* launch_tok_init(const float* iou_token, const float* mask_tokens, int nm, const float* sparse, int Ns, int R,
                             float* tokens, cudaStream_t stream) {
-  tok_init_kernel<<<R, 256, 0, stream>>>(iou_token, mask_tokens, nm, sparse, Ns, tokens);
+  launch_pdl(tok_init_kernel, dim3(R), dim3(256), 0, stream, 1, iou_token, mask_tokens, nm, sparse, Ns, tokens);
   return last_err();
 }
 
@@ -426,7 +434,7 @@ const char* launch_slice_copy(const float* in, int R, int C, int m0, int cnt, si
   if (total == 0) return nullptr;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  slice_copy_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(in, C, m0, cnt, inner, out, total);
+  launch_pdl(slice_copy_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, 1, in, C, m0, cnt, inner, out, total);
   return last_err();
 }
 

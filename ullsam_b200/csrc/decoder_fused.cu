@@ -413,6 +413,8 @@ dec_token_layer_kernel(DecTokLayer L, float* __restrict__ queries, const float* 
   const int rank = static_cast<int>(cluster_ctarank()), r = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   DT_BEGIN;
+  pdl_wait();
+  pdl_trigger();
   load_tokens(s, queries, tokens, r, nt, nr, !L.skip_pe);
   DT_STAMP("load");
 
@@ -517,6 +519,8 @@ dec_token_final_kernel(DecTokFinal F, float* __restrict__ queries, const float* 
   const Smem s = carve(smem_f, nr);
   const int rank = static_cast<int>(cluster_ctarank()), r = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
   load_tokens(s, queries, tokens, r, nt, nr, true);
   t2i_block(s, rank, nt, nr, F.tq_w, F.tq_b, F.to_w, F.to_b, F.nf_w, F.nf_b, proj + static_cast<size_t>(r) * 4096 * ldkv, ldkv, ns, warp,
             lane);
@@ -564,11 +568,6 @@ size_t fused_smem_bytes(int nr) {
   return (static_cast<size_t>(nr) * ROW_FLOATS + FIXED_FLOATS + fused_stages(nr) * T2I_STAGE_FLOATS) * sizeof(float);
 }
 
-const char* check_launch() {
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
-}
-
 }  // namespace
 
 bool dec_tokens_fused_supported(int Nt, int mlp_dim, int iou_hidden) {
@@ -582,8 +581,9 @@ const char* launch_dec_token_layer(const DecTokLayer& L, float* queries, const f
   const size_t smem = fused_smem_bytes(nr);
   static PerDeviceOnce configured;
   if (const char* e = set_max_smem_once(configured, dec_token_layer_kernel, static_cast<int>(fused_smem_bytes(kDecFusedMaxTokens)))) return e;
-  dec_token_layer_kernel<<<dim3(CL, R), FT, smem, stream>>>(L, queries, tokens, proj, ldkv, Nt, nr, fused_stages(nr), k128, v128);
-  return check_launch();
+  cudaError_t e = launch_pdl(dec_token_layer_kernel, dim3(CL, R), dim3(FT), smem, stream, 0, L, queries, tokens, proj, ldkv, Nt, nr,
+                             fused_stages(nr), k128, v128);
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
 const char* launch_dec_token_final(const DecTokFinal& F, float* queries, const float* tokens, const __nv_bfloat16* proj, int ldkv,
@@ -593,8 +593,9 @@ const char* launch_dec_token_final(const DecTokFinal& F, float* queries, const f
   const size_t smem = fused_smem_bytes(nr);
   static PerDeviceOnce configured;
   if (const char* e = set_max_smem_once(configured, dec_token_final_kernel, static_cast<int>(fused_smem_bytes(kDecFusedMaxTokens)))) return e;
-  dec_token_final_kernel<<<dim3(CL, R), FT, smem, stream>>>(F, queries, tokens, proj, ldkv, Nt, nr, fused_stages(nr), hyper, iou4);
-  return check_launch();
+  cudaError_t e = launch_pdl(dec_token_final_kernel, dim3(CL, R), dim3(FT), smem, stream, 0, F, queries, tokens, proj, ldkv, Nt, nr,
+                             fused_stages(nr), hyper, iou4);
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
 }  // namespace ullsam

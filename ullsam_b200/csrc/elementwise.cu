@@ -3,6 +3,7 @@
 #include "elementwise.h"
 
 #include "common.cuh"
+#include "host_util.h"
 
 namespace ullsam {
 
@@ -16,6 +17,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, float eps, int grid, int window,
                                                         int rows_out, __nv_bfloat16* __restrict__ y) {
   constexpr int DIM = VPL * 128;
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows_out) return;
@@ -78,16 +81,16 @@ const char* launch_layernorm(const float* x, const float* gamma, const float* be
   if (rows_out == 0) return nullptr;
   const int wpb = 8;
   const int blocks = (rows_out + wpb - 1) / wpb;
+  cudaError_t le = cudaSuccess;
   switch (dim) {
-    case 256: layernorm_kernel<2><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, eps, grid, window, rows_out, y); break;
-    case 768: layernorm_kernel<6><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, eps, grid, window, rows_out, y); break;
-    case 1024: layernorm_kernel<8><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, eps, grid, window, rows_out, y); break;
-    case 1280: layernorm_kernel<10><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, eps, grid, window, rows_out, y); break;
-    case 2048: layernorm_kernel<16><<<blocks, wpb * 32, 0, stream>>>(x, gamma, beta, eps, grid, window, rows_out, y); break;
+    case 256: le = launch_pdl(layernorm_kernel<2>, dim3(blocks), dim3(wpb * 32), 0, stream, 1, x, gamma, beta, eps, grid, window, rows_out, y); break;
+    case 768: le = launch_pdl(layernorm_kernel<6>, dim3(blocks), dim3(wpb * 32), 0, stream, 1, x, gamma, beta, eps, grid, window, rows_out, y); break;
+    case 1024: le = launch_pdl(layernorm_kernel<8>, dim3(blocks), dim3(wpb * 32), 0, stream, 1, x, gamma, beta, eps, grid, window, rows_out, y); break;
+    case 1280: le = launch_pdl(layernorm_kernel<10>, dim3(blocks), dim3(wpb * 32), 0, stream, 1, x, gamma, beta, eps, grid, window, rows_out, y); break;
+    case 2048: le = launch_pdl(layernorm_kernel<16>, dim3(blocks), dim3(wpb * 32), 0, stream, 1, x, gamma, beta, eps, grid, window, rows_out, y); break;
     default: return "layernorm: dim must be 256, 768, 1024, 1280 or 2048";
   }
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+  return le == cudaSuccess ? nullptr : cudaGetErrorString(le);
 }
 
 // ---------------------------------------------------------------------------------------------

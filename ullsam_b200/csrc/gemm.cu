@@ -65,19 +65,7 @@ static const char* launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, con
   if (const char* ce = set_max_smem_once(configured, kern, L::kTotal)) return ce;
   const int tiles = ((p.M + 255) / 256) * (p.N / 256);
   const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3((GEMM_EPI_WARP0 + EW) * 32);
-  cfg.dynamicSmemBytes = L::kTotal;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  cudaError_t e = launch_pdl(kern, dim3(2 * pairs), dim3((GEMM_EPI_WARP0 + EW) * 32), L::kTotal, stream, 2, ta, tb, p);
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -90,8 +78,7 @@ static const char* launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const 
   if (const char* ce = set_max_smem_once(configured, kern, L::kTotal)) return ce;
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * (p.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, GEMM_THREADS, L::kTotal, stream>>>(ta, tb, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::kTotal, stream, 1, ta, tb, p);
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -99,6 +86,13 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
   if (p.M <= 0) return nullptr;
   if (epi == EPI_BF16 && p.act == ACT_GELU && p.pos == nullptr) epi = EPI_GELU_BF16;
   else if (epi == EPI_GELU_BF16) return "gemm: EPI_GELU_BF16 is selected internally";
+  const bool stats = (epi == EPI_RES_STATS || epi == EPI_PATCH_STATS), fold = (epi == EPI_QKV_FOLD || epi == EPI_GELU_FOLD);
+  if (stats && (p.N % 256 != 0 || p.N > 128 * kStatSlots || !p.out2 || !p.row_stats || p.a_conv3))
+    return "gemm: the statistics epilogues need N % 256 == 0, N <= 1024, a plain A matrix, out2 and row_stats";
+  if (fold && (p.N % 256 != 0 || p.K % 256 != 0 || p.K > 128 * kStatSlots || !p.bias || !p.fold_s || !p.row_stats || p.a_conv3))
+    return "gemm: the folded-LayerNorm epilogues need N % 256 == 0, K % 256 == 0, K <= 1024, bias, fold_s and row_stats";
+  if (epi == EPI_QKV_FOLD && p.ln_partition && !p.pad_bias) return "gemm: EPI_QKV_FOLD with window scatter needs pad_bias";
+  if (epi == EPI_RES_STATS && !p.residual) return "gemm: EPI_RES_STATS needs residual";
   if (p.K % GEMM_BK != 0) return "gemm: K must be a multiple of 64";
   const bool ln = (epi == EPI_LN_BF16 || epi == EPI_LN_NCHW || epi == EPI_LN_RES || epi == EPI_UP1);
   int bn = (p.N % 256 == 0) ? 256 : 128;
@@ -121,11 +115,12 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
     if (!p.out2 || !p.ln_w || !p.ln_b || !p.residual) return "gemm: EPI_RES_LN needs residual, ln_w, ln_b and out2";
     if (p.ln_partition && p.M % 4096 != 0) return "gemm: EPI_RES_LN window partition needs whole 64x64 token grids";
   }
-  if (epi == EPI_QKV && p.ln_partition && (p.M % 4096 != 0 || p.T != 196))
+  if ((epi == EPI_QKV || epi == EPI_QKV_FOLD) && p.ln_partition && (p.M % 4096 != 0 || p.T != 196))
     return "gemm: EPI_QKV window scatter needs whole 64x64 token grids and T == 196";
   const bool pair = (epi == EPI_RES_LN) ||
                     (!pair_disabled && bn == 256 && !p.a_conv3 && p.M >= 4096 &&
-                     (epi == EPI_BF16 || epi == EPI_GELU_BF16 || epi == EPI_RES_F32 || epi == EPI_QKV));
+                     (epi == EPI_BF16 || epi == EPI_GELU_BF16 || epi == EPI_RES_F32 || epi == EPI_QKV || epi == EPI_RES_STATS ||
+                      epi == EPI_QKV_FOLD || epi == EPI_GELU_FOLD));
   e = make_tmap_2d_bf16(&tb, W, (uint64_t)p.N, (uint64_t)p.K, pair ? 128 : bn, GEMM_BK);
   if (e) return e;
   if (pair) {
@@ -139,6 +134,11 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
         return (ew16 & 2) ? launch_pair<EPI_RES_F32, 16>(ta, tb, p, num_sms, stream)
                           : launch_pair<EPI_RES_F32, 8>(ta, tb, p, num_sms, stream);
       case EPI_RES_LN: return launch_pair<EPI_RES_LN, 8>(ta, tb, p, num_sms, stream);
+      case EPI_RES_STATS: return launch_pair<EPI_RES_STATS, 8>(ta, tb, p, num_sms, stream);
+      case EPI_QKV_FOLD: return launch_pair<EPI_QKV_FOLD, 8>(ta, tb, p, num_sms, stream);
+      case EPI_GELU_FOLD:
+        return (ew16 & 1) ? launch_pair<EPI_GELU_FOLD, 16>(ta, tb, p, num_sms, stream)
+                          : launch_pair<EPI_GELU_FOLD, 8>(ta, tb, p, num_sms, stream);
       default:
         return (ew16 & 4) ? launch_pair<EPI_QKV, 16>(ta, tb, p, num_sms, stream)
                           : launch_pair<EPI_QKV, 8>(ta, tb, p, num_sms, stream);
@@ -156,6 +156,10 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
     ULLSAM_GEMM_CASE(EPI_QKV)
     ULLSAM_GEMM_CASE(EPI_PATCH)
     ULLSAM_GEMM_CASE(EPI_F32)
+    case EPI_RES_STATS: return launch_t<256, EPI_RES_STATS>(ta, tb, p, num_sms, stream);
+    case EPI_PATCH_STATS: return launch_t<256, EPI_PATCH_STATS>(ta, tb, p, num_sms, stream);
+    case EPI_QKV_FOLD: return launch_t<256, EPI_QKV_FOLD>(ta, tb, p, num_sms, stream);
+    case EPI_GELU_FOLD: return launch_t<256, EPI_GELU_FOLD>(ta, tb, p, num_sms, stream);
     case EPI_LN_RES:
       return launch_t<256, EPI_LN_RES>(ta, tb, p, num_sms, stream);
     case EPI_UP1:

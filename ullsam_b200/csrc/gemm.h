@@ -28,6 +28,18 @@ enum EpiMode : int {
                     // re-reads the rows it has just written (L2) and stores out2 = bf16 LN(x) (optionally in
                     // window-partitioned row order, image_encoder.py:243-264) — saves the HBM round trip of a separate
                     // LayerNorm kernel
+  // ---- LayerNorm folded into the GEMMs on either side of it (Block.norm1 / norm2, image_encoder.py:166-182) ----
+  //   LN(x) W^T + b  =  rstd * (x (gamma*W)^T  -  mean * s)  +  c,     s_n = sum_k gamma_k W_nk,   c_n = sum_k beta_k W_nk + b_n
+  // so the GEMM that PRODUCES the residual stream also emits a bf16 copy of it and per-row partial sums, and the GEMM that
+  // CONSUMES the normalised rows runs on the un-normalised copy with the weight gamma*W and finishes the LayerNorm in
+  // its epilogue.  No LayerNorm kernel, no second pass over the fp32 stream.
+  EPI_RES_STATS = 12,    // EPI_RES_F32, plus out2 = bf16(out) and row_stats[row][2 * n_blk + half] = (sum, sum of squares)
+                         // of the row's 128-column slice (fp32 values, before the bf16 rounding)
+  EPI_PATCH_STATS = 13,  // EPI_PATCH, same two extra outputs
+  EPI_QKV_FOLD = 14,     // EPI_QKV on the un-normalised rows: acc -> rstd * (acc - mean * fold_s[n]) + bias[n]; mean / rstd
+                         // of a row from the K / 128 partial sums in row_stats; pad_bias = the projection's own bias
+                         // (k / v rows of the window-padding tokens)
+  EPI_GELU_FOLD = 15,    // EPI_GELU_BF16, same
 };
 // EPI_BF16 / EPI_F32 also add pos[row % pos_rows][n] when p.pos != nullptr.
 
@@ -62,7 +74,12 @@ struct GemmParams {
   const float* hyper;  // EPI_MASK: hyper_in [R][4][32]
   int mask_m0;         // EPI_MASK: first mask channel written
   int mask_cnt;        // EPI_MASK: number of mask channels written (out is [R][mask_cnt][256][256] fp32)
+  float* row_stats;       // EPI_*_STATS (written) / EPI_*_FOLD (read): [M][kStatSlots] pairs (sum, sum of squares)
+  const float* fold_s;    // EPI_*_FOLD: [N] column sums of the bf16 weight gamma*W
+  const float* pad_bias;  // EPI_QKV_FOLD with ln_partition: [N] bias of the projection itself
 };
+
+constexpr int kStatSlots = 8;  // 128-column slices per row the statistics buffer has room for (LayerNorm dim <= 1024)
 
 // All return nullptr on success or a static error string.
 const char* make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,

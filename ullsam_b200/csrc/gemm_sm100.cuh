@@ -45,6 +45,17 @@ constexpr int GEMM_EPI_WARP0 = 4;
 #ifndef ULLSAM_GEMM_RELAXED_ARRIVE
 #define ULLSAM_GEMM_RELAXED_ARRIVE 1
 #endif
+// timing experiments only (wrong results): FOLD_DBG bit 0 = no row-statistics loads, bit 1 = no fold arithmetic;
+// STATS_DBG bit 0 = no bf16 copy, bit 1 = no partial sums
+#ifndef ULLSAM_FOLD_DBG
+#define ULLSAM_FOLD_DBG 0
+#endif
+#ifndef ULLSAM_STATS_DBG
+#define ULLSAM_STATS_DBG 0
+#endif
+#ifndef ULLSAM_FOLD_L2PF
+#define ULLSAM_FOLD_L2PF 1   // L2 prefetch of the next tile's row statistics, one tile period ahead
+#endif
 #ifndef ULLSAM_GEMM_WIDE_F32
 #define ULLSAM_GEMM_WIDE_F32 1  // fp32 epilogues: full 128-byte lines per row + addend loads one chunk ahead
 #endif
@@ -66,7 +77,7 @@ struct GemmSmem {
   static constexpr int kStageBytesPerWarp = 32 * 80;
   static constexpr int kStageOffset = (kScratchOffset + 4 * 128 * 4 + 15) / 16 * 16;
   // warp-private copy of the bias slice of the current tile (generic epilogues): up to 128 floats per epilogue warp
-  static constexpr int kBiasBytesPerWarp = 512;
+  static constexpr int kBiasBytesPerWarp = 1024;   // (second half: the column sums of the LayerNorm-folded epilogues)
   static constexpr int kBiasOffset = kStageOffset + EW * kStageBytesPerWarp;
   static constexpr int kTotal = kBiasOffset + EW * kBiasBytesPerWarp + 1024 /* alignment slack */;
   static_assert(kTotal <= 232448, "more than 227 KB of shared memory");
@@ -136,6 +147,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 "the LayerNorm / decoder epilogues assume two warps per row");
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel is built for 256-wide N tiles");
   static_assert(EPI != EPI_RES_LN || (BN == 256 && EW == 8), "EPI_RES_LN: 256-wide tiles, two 128-column halves per row");
+  // LayerNorm folded into the neighbouring GEMMs (gemm.h): kStats = producer side, kFold = consumer side
+  constexpr bool kStats = (EPI == EPI_RES_STATS || EPI == EPI_PATCH_STATS);
+  constexpr bool kFold = (EPI == EPI_QKV_FOLD || EPI == EPI_GELU_FOLD);
+  constexpr bool kIsQkv = (EPI == EPI_QKV || EPI == EPI_QKV_FOLD);
+  constexpr bool kIsGelu = (EPI == EPI_GELU_BF16 || EPI == EPI_GELU_FOLD);
+  constexpr bool kIsPatch = (EPI == EPI_PATCH || EPI == EPI_PATCH_STATS);
+  static_assert(!kStats || (BN == 256 && EW == 8), "statistics epilogues: 256-wide tiles, one 128-column slice per warp");
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   constexpr int S = L::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -160,7 +178,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // i-th tile of this CTA (pair).  Default: round robin over the N-fastest tile list.  EPI_RES_LN: M-major — all N tiles
   // of one row block are processed back to back by the same CTA pair, so its epilogue threads see whole rows.
   constexpr bool kMMajor = (EPI == EPI_RES_LN);
-  constexpr bool kRes = (EPI == EPI_RES_F32 || EPI == EPI_RES_LN);
+  constexpr bool kRes = (EPI == EPI_RES_F32 || EPI == EPI_RES_LN || EPI == EPI_RES_STATS);
   auto tile_at = [&](int i) -> int {
     if constexpr (kMMajor) return (tile0 + (i / tiles_n) * tile_step) * tiles_n + (i % tiles_n);
     else return tile0 + i * tile_step;
@@ -195,6 +213,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // (barriers, tensor memory and descriptors are set up; from here on the kernel reads what its predecessor wrote)
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -298,8 +319,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // c+1 — across the tile boundary, of the next tile's first chunk — is requested before chunk c is processed: its
     // DRAM latency is hidden behind a chunk of work or the wait for the accumulator (ncu before: 50 % of the
     // projection GEMM's epilogue samples were long-scoreboard stalls on these loads).
-    constexpr bool kAdd = kRes || EPI == EPI_PATCH;
-    constexpr bool kWide = ULLSAM_GEMM_WIDE_F32 && EW == 8 && (EPI == EPI_RES_F32 || EPI == EPI_PATCH || EPI == EPI_F32);
+    constexpr bool kAdd = kRes || kIsPatch;
+    constexpr bool kWide = ULLSAM_GEMM_WIDE_F32 && EW == 8 && (EPI == EPI_RES_F32 || EPI == EPI_PATCH || EPI == EPI_F32 || kStats);
+    static_assert(!kStats || kWide, "statistics epilogues are written for the full-line fp32 path");
+    // kStats: per-lane partial (sum, sum of squares) of the 8 rows this lane touches in the transposed phase ([h][i]: row
+    // h * 16 + i * 4 + lane / 8, columns (lane & 7) * 4 .. + 3 of every chunk), reduced over the 8 lanes at the end of the tile
+    float rs1[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, rs2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     constexpr bool kAddPipe = kWide && kAdd;
     static_assert(!kAddPipe || NCHUNK % 2 == 0, "addend double buffer: the buffer index must wrap at the tile boundary");
     float4 addbuf[2][2][4];
@@ -328,8 +353,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool bias_lane = p.bias != nullptr && lane * 4 < COLS_PER_WARP;
     static_assert(COLS_PER_WARP * 4 <= L::kBiasBytesPerWarp, "bias slice does not fit its shared-memory slot");
-    if (bias_lane && tile_at(0) < num_tiles)
+    float4 folds_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* folds_s = bias_s + 128;
+    static_assert(COLS_PER_WARP <= 128, "bias / column-sum slices: 128 floats each");
+    if (bias_lane && tile_at(0) < num_tiles) {
       bias_next = __ldg(reinterpret_cast<const float4*>(p.bias + (tile_at(0) % tiles_n) * BN + half * COLS_PER_WARP + lane * 4));
+      if constexpr (kFold)
+        folds_next = __ldg(reinterpret_cast<const float4*>(p.fold_s + (tile_at(0) % tiles_n) * BN + half * COLS_PER_WARP + lane * 4));
+    }
+#else
+    static_assert(!kFold, "the folded epilogues read their vectors from the shared-memory slots");
 #endif
     if constexpr (kAddPipe) {
       const int t0 = tile_at(0);
@@ -340,10 +373,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       prefetch_addend(tile_at(it + 1));
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const int row = m_blk * GEMM_BM + row_in_tile;
       const bool row_ok = row < p.M;
+      // kFold: the row's partial sums are requested before the wait for the accumulator (their latency hides behind it)
+      float fold_r = 1.f, fold_t = 0.f;   // rstd and -rstd * mean of this thread's row
+      float4 fst[kStatSlots / 2];
+      if constexpr (kFold) {
+        const float4* sp = reinterpret_cast<const float4*>(p.row_stats) + static_cast<size_t>(row_ok ? row : 0) * (kStatSlots / 2);
+        const int nsl = p.K >> 8;          // pairs of 128-column slices (K = LayerNorm dim, a multiple of 256)
+#pragma unroll
+        for (int j = 0; j < kStatSlots / 2; ++j)
+          fst[j] = (j < nsl && !(ULLSAM_FOLD_DBG & 1)) ? sp[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+#if ULLSAM_FOLD_L2PF
+        const int tn = tile_at(it + 1);
+        if (tn < num_tiles) {
+          const int rn = ((tn / tiles_n) * CG + cta_rank) * GEMM_BM + row_in_tile;
+          if (rn < p.M && rn != row) l2_prefetch_line(reinterpret_cast<const uint8_t*>(p.row_stats) + static_cast<size_t>(rn) * (kStatSlots * 8));
+        }
+#endif
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      if constexpr (kFold) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kStatSlots / 2; ++j) {   // fixed order: bit-reproducible whatever the producer's schedule was
+          s1 += fst[j].x; s2 += fst[j].y;
+          s1 += fst[j].z; s2 += fst[j].w;
+        }
+        const float inv_k = 1.0f / static_cast<float>(p.K);
+        const float mean = s1 * inv_k;
+        const float var = fmaxf(s2 * inv_k - mean * mean, 0.f);
+        fold_r = rsqrtf(var + p.ln_eps);
+        fold_t = -fold_r * mean;
+      }
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * COLS_PER_WARP;
       const int col0 = n_blk * BN + half * COLS_PER_WARP;
       // Hands this accumulator buffer back to the MMA warp.  The generic epilogues call it as soon as their last
@@ -585,16 +648,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           __syncwarp();  // every lane is done with the previous tile's slice
           if (bias_lane) {
             *reinterpret_cast<float4*>(bias_s + lane * 4) = bias_next;
+            if constexpr (kFold) *reinterpret_cast<float4*>(folds_s + lane * 4) = folds_next;
             const int tn = tile_at(it + 1);
-            if (tn < num_tiles)
+            if (tn < num_tiles) {
               bias_next = __ldg(reinterpret_cast<const float4*>(p.bias + (tn % tiles_n) * BN + half * COLS_PER_WARP + lane * 4));
+              if constexpr (kFold)
+                folds_next = __ldg(reinterpret_cast<const float4*>(p.fold_s + (tn % tiles_n) * BN + half * COLS_PER_WARP + lane * 4));
+            }
           }
           __syncwarp();
         }
 #endif
         const int rr = lane >> 2, cc = lane & 3;  // transposed phase: row-in-group, 16-byte column slot
         size_t qkv_row_off[4] = {0, 0, 0, 0};     // EPI_QKV: (g * heads * T + t) * 64 of the 4 rows this lane stores
-        if constexpr (EPI == EPI_QKV) {
+        if constexpr (kIsQkv) {
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int grow = tile_row0 + it * 8 + rr;
@@ -628,13 +695,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int ncol = col0 + chunk * 8;
             const int which = ncol / dim, rem = ncol - which * dim;
             if (which != 0 && tile_row0 < p.M) {
+              // (folded LayerNorm: p.bias holds W beta + b; the padding tokens are zero AFTER the norm, so they see b alone)
+              float4 b0, b1;
+              if constexpr (kFold) {
+                b0 = __ldg(reinterpret_cast<const float4*>(p.pad_bias + ncol));
+                b1 = __ldg(reinterpret_cast<const float4*>(p.pad_bias + ncol + 4));
+              } else {
 #if ULLSAM_GEMM_BIAS_SMEM
-              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + chunk * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + chunk * 8 + 4);
+                b0 = *reinterpret_cast<const float4*>(bias_s + chunk * 8);
+                b1 = *reinterpret_cast<const float4*>(bias_s + chunk * 8 + 4);
 #else
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol + 4));
+                b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol));
+                b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol + 4));
 #endif
+              }
               const uint4 val = make_uint4(pack_bf16(b0.x, b0.y), pack_bf16(b0.z, b0.w), pack_bf16(b1.x, b1.y), pack_bf16(b1.z, b1.w));
               __nv_bfloat16* base = (which == 1 ? p.k : p.v) + static_cast<size_t>(rem >> 6) * p.T * 64 + (rem & 63);
               for (int id = id0 + lane / CHUNKS; id < id1; id += TOK_PER_INST) {
@@ -659,7 +733,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // copies of it fall out of the instruction cache (measured: 972 -> 850 TFLOP/s when unrolled).
         // (16 epilogue warps: 96 registers, no room for two buffers; with the addend double buffer neither)
         // (keeping both double buffers was measured slower: proj 222 -> 234 us)
-        constexpr bool kPipe = (EPI != EPI_GELU_BF16) && EW == 8 && !kAddPipe;
+        constexpr bool kPipe = !kIsGelu && EW == 8 && !kAddPipe;
         uint32_t vbuf[2][32];
         if constexpr (kPipe) {
           tmem_ld32(taddr0, vbuf[0]);
@@ -709,7 +783,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
+          if constexpr (kFold && !(ULLSAM_FOLD_DBG & 2)) {
+            // LayerNorm finished here: rstd * (acc - mean * s_n) + c_n  (gemm.h)
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
+              const float4 s4 = *reinterpret_cast<const float4*>(folds_s + c * 32 + j);
+              f[j] = fmaf(f[j], fold_r, fmaf(fold_t, s4.x, b4.x));
+              f[j + 1] = fmaf(f[j + 1], fold_r, fmaf(fold_t, s4.y, b4.y));
+              f[j + 2] = fmaf(f[j + 2], fold_r, fmaf(fold_t, s4.z, b4.z));
+              f[j + 3] = fmaf(f[j + 3], fold_r, fmaf(fold_t, s4.w, b4.w));
+            }
+          } else if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
 #if ULLSAM_GEMM_BIAS_SMEM
@@ -720,7 +805,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
             }
           }
-          if constexpr (EPI == EPI_GELU_BF16) {
+          if constexpr (kIsGelu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = ((ULLSAM_GELU_RCP_MASK >> (j & 3)) & 1) ? gelu_erf_rcp(f[j]) : gelu_erf(f[j]);
           }
@@ -741,7 +826,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
           }
-          if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_QKV) {
+          if constexpr (EPI == EPI_BF16 || kIsGelu || kIsQkv) {
             // 32 bf16 per row = 64 bytes; staged with an 80-byte row pitch (conflict-free both ways)
             uint4* srow = reinterpret_cast<uint4*>(stage + lane * 80);
 #pragma unroll
@@ -751,7 +836,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
             size_t qkv_col_off = 0;
             __nv_bfloat16* qkv_base = nullptr;
-            if constexpr (EPI == EPI_QKV) {
+            if constexpr (kIsQkv) {
               const int dim = p.heads * 64;
               const int which = n0 / dim;
               const int rem = n0 - which * dim;
@@ -764,7 +849,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const int grow = tile_row0 + r_in;
               const uint4 val = *reinterpret_cast<const uint4*>(stage + r_in * 80 + cc * 16);
               if (grow < p.M) {
-                if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
+                if constexpr (EPI == EPI_BF16 || kIsGelu) {
                   *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(grow) * p.ldc + n0 + cc * 8) = val;
                 } else {
                   *reinterpret_cast<uint4*>(qkv_base + qkv_row_off[it] + qkv_col_off + cc * 8) = val;
@@ -794,6 +879,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     val.x += a.x; val.y += a.y; val.z += a.z; val.w += a.w;
                   }
                   *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(grow) * p.ldc + n0 + (lane & 7) * 4) = val;
+                  if constexpr (kStats) {
+                    // bf16 copy of the stream (the A operand of the GEMM behind the LayerNorm) + the row's partial sums
+                    if (!(ULLSAM_STATS_DBG & 1))
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + static_cast<size_t>(grow) * p.ldc + n0 + (lane & 7) * 4) =
+                        make_uint2(pack_bf16(val.x, val.y), pack_bf16(val.z, val.w));
+                    if (!(ULLSAM_STATS_DBG & 2)) {
+                    rs1[h][i] += (val.x + val.y) + (val.z + val.w);
+                    rs2[h][i] = fmaf(val.x, val.x, fmaf(val.y, val.y, fmaf(val.z, val.z, fmaf(val.w, val.w, rs2[h][i]))));
+                    }
+                  }
                 }
               }
               __syncwarp();
@@ -814,7 +909,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 float4 val = *reinterpret_cast<const float4*>(stage + r_in * 80 + cc * 16);
                 if (grow < p.M) {
                   const size_t off = static_cast<size_t>(grow) * p.ldc + n0 + h * 16 + cc * 4;
-                  if constexpr (kRes || EPI == EPI_PATCH) {
+                  if constexpr (kRes || kIsPatch) {
                     val.x += add[h][it].x; val.y += add[h][it].y; val.z += add[h][it].z; val.w += add[h][it].w;
                   }
                   if constexpr (EPI == EPI_RES_LN) {
@@ -836,6 +931,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       if constexpr (!kEarlyRelease) release_acc();
+      if constexpr (kStats && !(ULLSAM_STATS_DBG & 2)) {
+        // the 8 lanes that share a row (lane & 7 = 16-byte column slot) add up their partials; lane & 7 == 0 stores the pair
+        float2* dst = reinterpret_cast<float2*>(p.row_stats);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float a = rs1[h][i], b = rs2[h][i];
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              a += __shfl_xor_sync(0xffffffffu, a, o);
+              b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            const int grow = m_blk * GEMM_BM + quad * 32 + h * 16 + i * 4 + (lane >> 3);
+            if ((lane & 7) == 0 && grow < p.M) dst[static_cast<size_t>(grow) * kStatSlots + n_blk * 2 + half] = make_float2(a, b);
+            rs1[h][i] = 0.f;
+            rs2[h][i] = 0.f;
+          }
+      }
       if constexpr (EPI == EPI_RES_LN) {
         // ---- the LayerNorm that follows the residual add, once the last N tile of this row block is stored ----
         if (n_blk == tiles_n - 1) {

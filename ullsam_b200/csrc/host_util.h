@@ -5,8 +5,48 @@
 
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
+#include <utility>
 
 namespace ullsam {
+
+// Kernel launch, optionally with programmatic dependent launch (PDL): the ~2-3 us between two dependent kernels of a
+// stream (launch latency + ramp-up) overlap the tail of the predecessor; the kernel must call pdl_wait() (common.cuh)
+// before it touches global memory.  OFF by default (plain stream order), ULLSAM_PDL=1 turns the attribute on: measured on
+// B200 it does not move the 36 ms step (36.21 ms with, 36.10 ms without, same box — the kernels are ~300 us long and
+// persistent, there is no launch gap worth hiding), and one bench run with it on ended in the mbarrier watchdog of the
+// global attention kernel (never seen in plain stream order; not understood).  cluster_x > 1 adds a
+// cluster dimension.
+inline bool pdl_enabled() {
+  static const bool on = getenv("ULLSAM_PDL") != nullptr && atoi(getenv("ULLSAM_PDL")) != 0;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // "Has this kernel been configured on the CURRENT device yet?"  cudaFuncSetAttribute is per device (context), so a
 // process that drives several GPUs has to set MaxDynamicSharedMemorySize on each of them; one flag bit per device,

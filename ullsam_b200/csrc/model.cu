@@ -50,7 +50,38 @@ struct EncBlock {
   float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *qkv_b, *proj_b, *lin1_b, *lin2_b;
   bf16 *qkv_w, *proj_w, *lin1_w, *lin2_w, *relh, *relw;
   bool global;
+  // LayerNorm folded into the projection behind it (gemm.h, EPI_*_FOLD): fp32 copies of the two weights, and what
+  // fold_encoder_weights() derives from them and the norm's affine parameters
+  float *qkv_w32, *lin1_w32;
+  bf16 *qkv_wf, *lin1_wf;                   // bf16(gamma * W)
+  float *qkv_s, *qkv_c, *lin1_s, *lin1_c;   // s_n = sum_k Wf_nk,  c_n = sum_k beta_k W_nk + b_n
 };
+
+// Wf = bf16(gamma * W), s = row sums of Wf (as rounded: the epilogue subtracts mean * s from an accumulator that was built
+// from exactly these values), c = W beta + b (fp32 W).  One warp per output row.
+__global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ w32, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ bias, int N, int K,
+                                                      bf16* __restrict__ wf, float* __restrict__ s_out, float* __restrict__ c_out) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float ss = 0.f, cc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = w32[static_cast<size_t>(n) * K + k];
+    const bf16 r = __float2bfloat16(gamma[k] * w);
+    wf[static_cast<size_t>(n) * K + k] = r;
+    ss += __bfloat162float(r);
+    cc = fmaf(beta[k], w, cc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    cc += __shfl_xor_sync(0xffffffffu, cc, o);
+  }
+  if (lane == 0) {
+    s_out[n] = ss;
+    c_out[n] = cc + bias[n];
+  }
+}
 
 struct DecAttnTok {  // token-side projections kept in fp32
   float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b;
@@ -80,6 +111,12 @@ struct ullsam_handle {
   // weight upload: copies and re-pack kernels run on the legacy default stream without a host sync per tensor; the first
   // forward call after an upload makes its stream wait for `weights_ev`
   bool weights_dirty = false;
+  bool enc_fold_dirty = true;   // an encoder tensor changed since fold_encoder_weights() last ran
+  int ln_fold = 1;              // LayerNorm folded into the GEMMs around it: bit 0 = Block.norm1 (mlp.lin2 / patch embedding ->
+                                // attn.qkv), bit 1 = Block.norm2 (attn.proj -> mlp.lin1).  ULLSAM_LN_FOLD overrides; 0 = separate
+                                // LayerNorm kernels.  Default 1: measured on B200 (tools/time_gemm_fold.py, ViT-B, batch 32) norm1's
+                                // fold costs lin2 +15 us and qkv +23 us for a 90 us LayerNorm kernel, norm2's costs proj +75 us
+                                // (HBM-bound: the extra bf16 copy is exposed) and lin1 +47 us (GELU epilogue, instruction-bound)
   cudaStream_t weights_stream = 0;
   cudaEvent_t weights_ev = nullptr;
   float* staging = nullptr;
@@ -110,7 +147,8 @@ struct ullsam_handle {
   float* x = nullptr;
   bf16 *q = nullptr, *k = nullptr, *v = nullptr, *ao = nullptr, *hid = nullptr;
   float* kmax = nullptr;  // [kEncChunk * heads] max key norm per (image, head): scratch of the global attention
-  bf16* xn_t = nullptr;  // LayerNorm outputs in token order (xn holds the window-partitioned ones: its pad rows stay zero)
+  bf16* xn_t = nullptr;  // LayerNorm outputs in token order; with the folded LayerNorm: the bf16 copy of the residual stream
+  float* row_stats = nullptr;  // [tok][kStatSlots][2] partial (sum, sum of squares) per row and 128-column slice
   float* emb_f32 = nullptr;  // [cap,256,4096] when the caller wants bf16 output / host staging
   int dec_cap_r = 0, dec_cap_nt = 0;
   float *tokens = nullptr, *queries = nullptr, *tq = nullptr, *tk = nullptr, *tv = nullptr, *ta = nullptr, *tmp = nullptr,
@@ -249,6 +287,19 @@ void reg_custom(ullsam_handle* h, const std::string& key, std::vector<int64_t> s
   h->slots[key] = std::move(s);
 }
 
+// a projection weight that is kept twice: bf16 (the GEMM operand of the unfolded path) and fp32 (source of the LayerNorm fold)
+void reg_w_with_f32(ullsam_handle* h, const std::string& key, int64_t N, int64_t K, bf16** w_bf16, float** w_f32) {
+  const size_t n = static_cast<size_t>(N) * K;
+  bf16* d0 = dalloc<bf16>(h, n);
+  float* d1 = dalloc<float>(h, n);
+  *w_bf16 = d0;
+  *w_f32 = d1;
+  reg_custom(h, key, {N, K}, 0, [d0, d1, n](const float* src) -> const char* {
+    if (const char* e = pack<bf16>(src, d0, 1, 1, 1, static_cast<int>(n), 0, 0, 0, 1)) return e;
+    return pack<float>(src, d1, 1, 1, 1, static_cast<int>(n), 0, 0, 0, 1);
+  });
+}
+
 bool is_global(const ullsam_config& c, int i) {
   for (int j = 0; j < c.num_global; ++j)
     if (c.global_attn_indexes[j] == i) return true;
@@ -272,11 +323,17 @@ void register_encoder(ullsam_handle* h) {
     reg_plain<float>(h, bp + "norm1.bias", {D}, 0, &b.ln1_b);
     reg_plain<float>(h, bp + "norm2.weight", {D}, 0, &b.ln2_w);
     reg_plain<float>(h, bp + "norm2.bias", {D}, 0, &b.ln2_b);
-    reg_plain<bf16>(h, bp + "attn.qkv.weight", {3 * D, D}, 0, &b.qkv_w);
+    reg_w_with_f32(h, bp + "attn.qkv.weight", 3 * D, D, &b.qkv_w, &b.qkv_w32);
+    b.qkv_wf = dalloc<bf16>(h, 3 * D * D);
+    b.qkv_s = dalloc<float>(h, 3 * D);
+    b.qkv_c = dalloc<float>(h, 3 * D);
     reg_plain<float>(h, bp + "attn.qkv.bias", {3 * D}, 0, &b.qkv_b);
     reg_plain<bf16>(h, bp + "attn.proj.weight", {D, D}, 0, &b.proj_w);
     reg_plain<float>(h, bp + "attn.proj.bias", {D}, 0, &b.proj_b);
-    reg_plain<bf16>(h, bp + "mlp.lin1.weight", {M, D}, 0, &b.lin1_w);
+    reg_w_with_f32(h, bp + "mlp.lin1.weight", M, D, &b.lin1_w, &b.lin1_w32);
+    b.lin1_wf = dalloc<bf16>(h, M * D);
+    b.lin1_s = dalloc<float>(h, M);
+    b.lin1_c = dalloc<float>(h, M);
     reg_plain<float>(h, bp + "mlp.lin1.bias", {M}, 0, &b.lin1_b);
     reg_plain<bf16>(h, bp + "mlp.lin2.weight", {D, M}, 0, &b.lin2_w);
     reg_plain<float>(h, bp + "mlp.lin2.bias", {D}, 0, &b.lin2_b);
@@ -448,7 +505,7 @@ int check_ready(ullsam_handle* h, int which) {
 int ensure_encoder_ws(ullsam_handle* h, int B) {
   if (B <= h->enc_cap) return ULLSAM_OK;
   for (void* p : {(void*)h->x, (void*)h->xn_t, (void*)h->kmax, (void*)h->q, (void*)h->k, (void*)h->v, (void*)h->ao, (void*)h->hid,
-                  (void*)h->emb_f32})
+                  (void*)h->emb_f32, (void*)h->row_stats})
     dfree(h, p);
   const size_t D = h->cfg.embed_dim, M = h->cfg.mlp_dim;
   const size_t tokw = static_cast<size_t>(B) * 4900, tok = static_cast<size_t>(B) * 4096;
@@ -461,7 +518,8 @@ int ensure_encoder_ws(ullsam_handle* h, int B) {
   h->ao = dalloc<bf16>(h, tok * D);
   h->hid = dalloc<bf16>(h, tok * (M > 768 ? M : 768));
   h->emb_f32 = dalloc<float>(h, tok * 256);
-  if (!h->x || !h->xn_t || !h->kmax || !h->q || !h->k || !h->v || !h->ao || !h->hid || !h->emb_f32) {
+  h->row_stats = dalloc<float>(h, tok * kStatSlots * 2);
+  if (!h->row_stats || !h->x || !h->xn_t || !h->kmax || !h->q || !h->k || !h->v || !h->ao || !h->hid || !h->emb_f32) {
     h->enc_cap = 0;
     return fail(h, ULLSAM_ERR_NOMEM, "cudaMalloc failed for the encoder workspace");
   }
@@ -527,6 +585,22 @@ GemmParams gp(int M, int N, int K) {
   return p;
 }
 
+// Block.norm1 / norm2 folded into attn.qkv / mlp.lin1 (gemm.h): re-derived whenever an encoder tensor has been uploaded.
+// Runs on the stream of the forward call that finds the flag set and is drained before that call goes on, so forward
+// calls on other streams see the folded weights too (uploads are rare; one host sync per upload batch).
+int fold_encoder_weights(ullsam_handle* h, cudaStream_t st) {
+  if (!h->enc_fold_dirty || !h->ln_fold) return ULLSAM_OK;
+  const int D = h->cfg.embed_dim, MD = h->cfg.mlp_dim;
+  for (EncBlock& b : h->blocks) {
+    fold_ln_kernel<<<(3 * D + 7) / 8, 256, 0, st>>>(b.qkv_w32, b.ln1_w, b.ln1_b, b.qkv_b, 3 * D, D, b.qkv_wf, b.qkv_s, b.qkv_c);
+    fold_ln_kernel<<<(MD + 7) / 8, 256, 0, st>>>(b.lin1_w32, b.ln2_w, b.ln2_b, b.lin1_b, MD, D, b.lin1_wf, b.lin1_s, b.lin1_c);
+  }
+  CKC(cudaGetLastError());
+  CKC(cudaStreamSynchronize(st));
+  h->enc_fold_dirty = false;
+  return ULLSAM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // ImageEncoderViT.forward for Bc <= kEncChunk images (image_encoder.py:106-116)
 // ---------------------------------------------------------------------------------------------------
@@ -534,12 +608,21 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
   const auto& c = h->cfg;
   const int D = c.embed_dim, MD = c.mlp_dim, heads = c.num_heads, sms = h->sms;
   const int tok = Bc * 4096;
+  // LayerNorm folded into the GEMMs on either side of it (default): every GEMM that writes the residual stream (patch
+  // embedding, attn.proj, mlp.lin2) also writes its bf16 copy and per-row partial sums, and attn.qkv / mlp.lin1 run on that
+  // copy with gamma-scaled weights and finish the normalisation in their epilogue — no LayerNorm kernel, no cast before
+  // the neck.  (D % 256 == 0 and D <= 1024: ViT-B and ViT-L.)
+  const bool foldable = D % 256 == 0 && D <= 128 * kStatSlots;
+  const bool fold1 = foldable && (h->ln_fold & 1), fold2 = foldable && (h->ln_fold & 2);
+  if (fold1 || fold2)
+    if (int rc = fold_encoder_weights(h, st)) return rc;
   // PatchEmbed (+ pos_embed)
   CKS(launch_im2col16(images, dtype == ULLSAM_BF16, Bc, 3, 1024, h->hid, st));
   {
     GemmParams p = gp(tok, D, 768);
     p.bias = h->patch_b; p.out = h->x; p.pos = h->pos; p.pos_rows = 4096;
-    CKS(launch_gemm(EPI_PATCH, h->hid, h->patch_w, p, sms, st));
+    if (fold1) { p.out2 = h->xn_t; p.row_stats = h->row_stats; }
+    CKS(launch_gemm(fold1 ? EPI_PATCH_STATS : EPI_PATCH, h->hid, h->patch_w, p, sms, st));
     mark(h, PC_PATCH, st, 2);
   }
   // The LayerNorms that follow a residual add (norm2 after the attention branch, the next block's norm1 after the MLP
@@ -551,7 +634,7 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
   static const int fuse_env = getenv("ULLSAM_LN_FUSION") ? atoi(getenv("ULLSAM_LN_FUSION")) : 0;
   // (the fused epilogue is built for 256-wide N tiles of at most 1024 columns: ViT-B and ViT-L)
   const bool fusable = D % 256 == 0 && D <= 1024;
-  const bool fuse_ln1 = fusable && (fuse_env & 1), fuse_ln2 = fusable && (fuse_env & 2);
+  const bool fuse_ln1 = !fold1 && fusable && (fuse_env & 1), fuse_ln2 = !fold2 && fusable && (fuse_env & 2);
   for (int i = 0; i < c.depth; ++i) {
     const EncBlock& b = h->blocks[i];
     const int win = b.global ? 0 : c.window_size;
@@ -559,14 +642,17 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
     // norm1 output stays in token order for windowed blocks too: window_partition (image_encoder.py:168-172, 243-264) is
     // done by the QKV epilogue on the store, so the GEMM runs on the 4096 image tokens instead of the 4900 padded ones
     // (-16 % of its rows); the constant k / v rows of the 804 padding tokens (= qkv.bias) ride on the same epilogue.
-    if (i == 0 || !fuse_ln1) {
+    if (!fold1 && (i == 0 || !fuse_ln1)) {
       CKS(launch_layernorm(h->x, b.ln1_w, b.ln1_b, c.enc_ln_eps, Bc, 64, D, 0, h->xn_t, st));
       mark(h, PC_LN, st);
     }
-    {  // qkv + head split (+ window_partition)
+    {  // (norm1 +) qkv + head split (+ window_partition)
       GemmParams p = gp(tok, 3 * D, D);
       p.bias = b.qkv_b; p.q = h->q; p.k = h->k; p.v = h->v; p.T = T; p.heads = heads; p.ln_partition = win ? 1 : 0;
-      CKS(launch_gemm(EPI_QKV, h->xn_t, b.qkv_w, p, sms, st));
+      if (fold1) {
+        p.bias = b.qkv_c; p.fold_s = b.qkv_s; p.pad_bias = b.qkv_b; p.row_stats = h->row_stats; p.ln_eps = c.enc_ln_eps;
+      }
+      CKS(launch_gemm(fold1 ? EPI_QKV_FOLD : EPI_QKV, h->xn_t, fold1 ? b.qkv_wf : b.qkv_w, p, sms, st));
       mark(h, PC_GEMM_QKV, st);
     }
     // attention (+ rel-pos bias, + window_unpartition)
@@ -578,17 +664,19 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
       if (fuse_ln2) {
         p.ln_w = b.ln2_w; p.ln_b = b.ln2_b; p.ln_eps = c.enc_ln_eps; p.out2 = h->xn_t; p.ln_partition = 0;
       }
-      CKS(launch_gemm(fuse_ln2 ? EPI_RES_LN : EPI_RES_F32, h->ao, b.proj_w, p, sms, st));
+      if (fold2) { p.out2 = h->xn_t; p.row_stats = h->row_stats; }
+      CKS(launch_gemm(fold2 ? EPI_RES_STATS : (fuse_ln2 ? EPI_RES_LN : EPI_RES_F32), h->ao, b.proj_w, p, sms, st));
       mark(h, PC_GEMM_PROJ, st);
     }
-    if (!fuse_ln2) {
+    if (!fold2 && !fuse_ln2) {
       CKS(launch_layernorm(h->x, b.ln2_w, b.ln2_b, c.enc_ln_eps, Bc, 64, D, 0, h->xn_t, st));
       mark(h, PC_LN, st);
     }
     {  // MLP
       GemmParams p = gp(tok, MD, D);
       p.bias = b.lin1_b; p.out = h->hid; p.act = ACT_GELU;
-      CKS(launch_gemm(EPI_BF16, h->xn_t, b.lin1_w, p, sms, st));
+      if (fold2) { p.bias = b.lin1_c; p.fold_s = b.lin1_s; p.row_stats = h->row_stats; p.ln_eps = c.enc_ln_eps; }
+      CKS(launch_gemm(fold2 ? EPI_GELU_FOLD : EPI_BF16, h->xn_t, fold2 ? b.lin1_wf : b.lin1_w, p, sms, st));
       mark(h, PC_GEMM_LIN1, st);
     }
     {  // lin2 + residual (+ the next block's norm1 and window_partition)
@@ -600,12 +688,13 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
         p.ln_w = nb.ln1_w; p.ln_b = nb.ln1_b; p.ln_eps = c.enc_ln_eps;
         p.out2 = h->xn_t; p.ln_partition = 0;
       }
-      CKS(launch_gemm(fuse_next ? EPI_RES_LN : EPI_RES_F32, h->hid, b.lin2_w, p, sms, st));
+      if (fold1) { p.out2 = h->xn_t; p.row_stats = h->row_stats; }   // (the last block's copy feeds the neck)
+      CKS(launch_gemm(fold1 ? EPI_RES_STATS : (fuse_next ? EPI_RES_LN : EPI_RES_F32), h->hid, b.lin2_w, p, sms, st));
       mark(h, PC_GEMM_LIN2, st);
     }
   }
   // neck: 1x1 conv -> LayerNorm2d -> 3x3 conv -> LayerNorm2d, NCHW out
-  CKS(launch_cast_f32_bf16(h->x, static_cast<size_t>(tok) * D, h->xn_t, st));
+  if (!fold1) CKS(launch_cast_f32_bf16(h->x, static_cast<size_t>(tok) * D, h->xn_t, st));
   {
     GemmParams p = gp(tok, 256, D);
     p.out = h->q; p.ln_w = h->neck1_w; p.ln_b = h->neck1_b; p.ln_eps = 1e-6f;
@@ -616,7 +705,7 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
     p.a_conv3 = 1; p.conv_c = 256;
     p.out = out_f32; p.ln_w = h->neck3_w; p.ln_b = h->neck3_b; p.ln_eps = 1e-6f; p.hw = 4096;
     CKS(launch_gemm(EPI_LN_NCHW, h->q, h->neck2_w, p, sms, st));
-    mark(h, PC_NECK, st, 3);
+    mark(h, PC_NECK, st, fold1 ? 2 : 3);
   }
   return ULLSAM_OK;
 }
@@ -876,6 +965,7 @@ int ullsam_create(const ullsam_config* cfg, int device, ullsam_handle** out) {
   h->cfg = *cfg;
   h->device = device;
   h->sms = prop.multiProcessorCount;
+  if (getenv("ULLSAM_LN_FOLD") != nullptr) h->ln_fold = atoi(getenv("ULLSAM_LN_FOLD")) & 3;
   if (cfg->depth > 0) register_encoder(h);  // depth == 0: decoder-only handle (MaskDecoder / TwoWayTransformer shims)
   register_decoder(h);
   if (h->alloc_failed) {
@@ -949,6 +1039,7 @@ int set_weight_impl(ullsam_handle* h, const char* key, const void* data, int dty
   g_pack_stream = 0;
   if (pe) return fail(h, ULLSAM_ERR_CUDA, pe);
   h->weights_dirty = true;
+  if (s.which == 0) h->enc_fold_dirty = true;
   s.loaded = true;
   return ULLSAM_OK;
 }

@@ -63,9 +63,14 @@ def gemm(
     conv3: bool = False,
     out2: Optional[torch.Tensor] = None,
     ln_partition: bool = False,
+    row_stats: Optional[torch.Tensor] = None,
+    fold_s: Optional[torch.Tensor] = None,
+    pad_bias: Optional[torch.Tensor] = None,
 ) -> Optional[torch.Tensor]:
     """C = A[M,K] @ W[N,K]^T with the epilogue selected by ``epi`` (see include/ullsam.h)."""
-    _require_cuda(a, w, bias, out, residual, pos, ln_w, ln_b, out2)
+    _require_cuda(a, w, bias, out, residual, pos, ln_w, ln_b, out2, row_stats, fold_s, pad_bias)
+    if row_stats is not None:  # fp32 [M, STAT_SLOTS, 2]: (sum, sum of squares) per row and 128-column slice
+        assert row_stats.dtype == torch.float32 and row_stats.is_contiguous() and row_stats.numel() == a.shape[0] * _lib.STAT_SLOTS * 2
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
     N, K = w.shape
     if conv3:
@@ -81,13 +86,13 @@ def gemm(
     d.A, d.W, d.bias = ptr(a), ptr(w), ptr(bias)
     d.act = act
     d.ldc = N
-    if epi == _lib.EPI_QKV:
+    if epi in (_lib.EPI_QKV, _lib.EPI_QKV_FOLD):
         q, k, v = qkv
         d.q, d.k, d.v, d.T, d.heads = ptr(q), ptr(k), ptr(v), T, heads
         # ln_partition: A's rows are image tokens [B,64,64]; the store window-partitions them (pad rows not written)
     else:
         if out is None:
-            if epi in (_lib.EPI_BF16, _lib.EPI_LN_BF16):
+            if epi in (_lib.EPI_BF16, _lib.EPI_LN_BF16, _lib.EPI_GELU_FOLD):
                 out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
             elif epi == _lib.EPI_LN_NCHW:
                 out = torch.empty((M // hw, N, hw), dtype=torch.float32, device=a.device)
@@ -99,6 +104,7 @@ def gemm(
     d.pos_rows = pos.shape[0] if pos is not None else 0
     d.ln_w, d.ln_b, d.ln_eps, d.hw = ptr(ln_w), ptr(ln_b), ln_eps, hw
     d.out2, d.ln_partition = ptr(out2), int(ln_partition)
+    d.row_stats, d.fold_s, d.pad_bias = ptr(row_stats), ptr(fold_s), ptr(pad_bias)
     check(_lib.load().ullsam_op_gemm(C.byref(d), current_stream_ptr(a.device)), what="ullsam_op_gemm")
     return out
 
