@@ -23,4 +23,8 @@ cap attn14 "windowed_attention_kernel" 2 python tools/time_attention.py
 cap dectok "dec_token_layer_kernel" 3 python tools/time_decoder.py 3
 cap decfin "dec_token_final_kernel" 1 python tools/time_decoder.py 3
 cap qkv_vitl "gemm_kernel<.int.256, .int.2," 6 python tools/time_gemm_vitl.py
+# LayerNorm-folded GEMMs (ViT-B, batch 32): the consumer (qkv, epilogue 14) and the producer with K = 3072 (lin2, epilogue 12; the
+# first two matches are the K = 768 launches of the proj shape, so skip 12 = 10 proj + 2 lin2 warm-ups)
+cap qkv_fold "gemm_kernel<.int.256, .int.14," 4 python tools/time_gemm_fold.py
+cap lin2_stats "gemm_kernel<.int.256, .int.12," 12 python tools/time_gemm_fold.py
 ls -la gpurun_out/ | grep ${TAG}

@@ -947,20 +947,33 @@ __global__ void __launch_bounds__(256) k_norm_max_kernel(const __nv_bfloat16* __
   pdl_wait();
   pdl_trigger();
   const uint4* base = reinterpret_cast<const uint4*>(k + static_cast<size_t>(blockIdx.x) * T * 64);
+  // 8 lanes per key row (16 bytes each): every load instruction of a warp covers four whole 128-byte rows; the squared norm
+  // of a row is the sum over its 8 lanes.  Four independent loads per lane in flight.
+  const int sub = threadIdx.x & 7, rgrp = threadIdx.x >> 3;   // 32 row groups per CTA
   float mx = 0.f;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+  auto sq8 = [](const uint4& u) {
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
     float qq = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 u = __ldg(base + static_cast<size_t>(t) * 8 + c);
-      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f2 = __bfloat1622float2(b2[e]);
-        qq = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, qq));
-      }
+    for (int e = 0; e < 4; ++e) {
+      const float2 f2 = __bfloat1622float2(b2[e]);
+      qq = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, qq));
     }
-    mx = fmaxf(mx, qq);
+    return qq;
+  };
+  for (int t0 = rgrp; t0 < T; t0 += 128) {      // rows t0, t0 + 32, t0 + 64, t0 + 96
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      u[i] = (t0 + 32 * i < T) ? __ldg(base + static_cast<size_t>(t0 + 32 * i) * 8 + sub) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float qq = sq8(u[i]);
+      qq += __shfl_xor_sync(0xffffffffu, qq, 1);
+      qq += __shfl_xor_sync(0xffffffffu, qq, 2);
+      qq += __shfl_xor_sync(0xffffffffu, qq, 4);
+      mx = fmaxf(mx, qq);
+    }
   }
   mx = warp_max(mx);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;

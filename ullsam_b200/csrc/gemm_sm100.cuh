@@ -36,6 +36,12 @@ constexpr int GEMM_EPI_WARP0 = 4;
                                   // polynomial form on 1/4, 1/2, 3/4 or all of the elements: 489, 494, 502, 501 us against 490 —
                                   // the epilogue is bound by its instruction count, not by the special-function unit.)
 #endif
+#ifndef ULLSAM_GELU_LOGISTIC
+#define ULLSAM_GELU_LOGISTIC 1   // lin1's GELU as gelu_logistic() (common.cuh: |error| <= 2.6e-5, 9 instructions) instead of the A&S erf (13)
+#endif
+#ifndef ULLSAM_GELU_PIPE
+#define ULLSAM_GELU_PIPE 0   // 1: the 8-warp GELU epilogue also double-buffers its TMEM loads (fully unrolled chunk loop)
+#endif
 #ifndef ULLSAM_GEMM_EARLY_RELEASE
 #define ULLSAM_GEMM_EARLY_RELEASE 1
 #endif
@@ -733,7 +739,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // copies of it fall out of the instruction cache (measured: 972 -> 850 TFLOP/s when unrolled).
         // (16 epilogue warps: 96 registers, no room for two buffers; with the addend double buffer neither)
         // (keeping both double buffers was measured slower: proj 222 -> 234 us)
-        constexpr bool kPipe = !kIsGelu && EW == 8 && !kAddPipe;
+        constexpr bool kPipe = (!kIsGelu || ULLSAM_GELU_PIPE) && EW == 8 && !kAddPipe;
         uint32_t vbuf[2][32];
         if constexpr (kPipe) {
           tmem_ld32(taddr0, vbuf[0]);
@@ -806,8 +812,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           if constexpr (kIsGelu) {
+#if ULLSAM_GELU_LOGISTIC
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_logistic(f[j]);
+#else
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = ((ULLSAM_GELU_RCP_MASK >> (j & 3)) & 1) ? gelu_erf_rcp(f[j]) : gelu_erf(f[j]);
+#endif
           }
           if constexpr (EPI == EPI_BF16 || EPI == EPI_F32) {
             if (p.pos != nullptr) {
