@@ -191,6 +191,9 @@ typedef struct {
   float* row_stats;      /* epi 12, 13 (written), 14, 15 (read): fp32 [M][8][2] */
   const float* fold_s;   /* epi 14, 15: [N] */
   const float* pad_bias; /* epi 14 with ln_partition: [N] */
+  float* kmax_sq;        /* epi 2, 14 (optional, rows in group order, T % 32 == 0): [M / T][heads], zeroed by the caller; the epilogue
+                          * folds max |k row|^2 per (group, head) into it (atomicMax on the float bits) — the key-norm bound of
+                          * the global attention, which otherwise takes a pre-pass over K */
 } ullsam_gemm_desc;
 int ullsam_op_gemm(const ullsam_gemm_desc* d, void* stream);
 

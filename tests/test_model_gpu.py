@@ -67,6 +67,35 @@ def test_encoder_vs_reference_golden(ctx):
     assert e <= 1e-2
 
 
+def test_folded_layernorm_follows_a_weight_upload():
+    """The encoder folds Block.norm1 into attn.qkv (gamma-scaled weight, column sums, W beta + b: csrc/model.cu
+    fold_encoder_weights).  Those derived tensors must be rebuilt when ANY of their sources is uploaded again, alone and in
+    any order: a new norm1.weight / norm1.bias, then a new qkv.weight, each checked against the oracle on the modified
+    state dict (and shown to differ from the previous result, so a stale fold could not pass)."""
+    from ullsam_b200.engine import Engine
+
+    cfg = O.config("vit_b")
+    sd = dict(synth.make_state_dict(cfg, 77))
+    eng = Engine(model="vit_b")
+    eng.load_state_dict(sd)
+    images, _ = synth.make_images(1, 1024, seed=78)
+    g = torch.Generator().manual_seed(79)
+    prev = eng.encoder_forward(images.cuda()).cpu()
+    for keys in (("image_encoder.blocks.0.norm1.weight", "image_encoder.blocks.5.norm1.bias"), ("image_encoder.blocks.3.attn.qkv.weight",)):
+        for k in keys:
+            t = sd[k]
+            sd[k] = (t * 1.5 + 0.3 * torch.randn(t.shape, generator=g)) if t.dim() == 1 else t + 0.02 * torch.randn(t.shape, generator=g)
+            eng.set_weight(k, sd[k])
+        got = eng.encoder_forward(images.cuda()).cpu()
+        with torch.no_grad():
+            ref = O.encoder_forward(sd, images, cfg)
+        e, moved = rel_l2(got, ref), rel_l2(got, prev)
+        print(f"after re-uploading {keys}: rel-L2 vs oracle {e:.3e}, vs the previous output {moved:.3e}")
+        assert e <= 1e-2 and moved >= 3e-2
+        prev = got
+    eng.close()
+
+
 def test_encoder_is_batch_invariant_across_chunks(ctx):
     """Full-size property (BASELINE.json's batch of 32 and beyond): an image's embedding does not depend on where it
     sits in the batch — 34 images (two 32-image workspace chunks: 32 + 2) made of two distinct images must reproduce the

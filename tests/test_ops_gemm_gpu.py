@@ -111,6 +111,25 @@ def test_gemm_qkv_split(T, G):
         _close(got, r, 8e-3, f"qkv[{name}] T={T}")
 
 
+def test_gemm_qkv_key_norm_maximum():
+    """EPI_QKV with kmax_sq: the epilogue also folds max_t |k[g][head][t]|^2 into a [G][heads] buffer (the a-priori score
+    bound of the global attention, attention.cu) — the values are the fp32 ones before the bf16 rounding of the store."""
+    from ullsam_b200 import _lib, ops
+
+    T, G, heads, dim = 4096, 2, 12, 768
+    a, w, b = _mk(G * T - 100, 3 * dim, dim, 6)          # the last group is short: its missing rows must not contribute
+    q = torch.zeros(G, heads, T, 64, dtype=torch.bfloat16, device="cuda")
+    k, v = torch.zeros_like(q), torch.zeros_like(q)
+    kmax = torch.zeros(G, heads, device="cuda")
+    ops.gemm(a, w, b, epi=_lib.EPI_QKV, qkv=(q, k, v), T=T, heads=heads, kmax_sq=kmax)
+    torch.cuda.synchronize()
+    kk = (_ref(a, w, b)[:, dim:2 * dim]).reshape(-1, heads, 64)
+    rows = torch.arange(kk.shape[0], device="cuda") // T
+    want = torch.stack([(kk[rows == g] ** 2).sum(-1).amax(0) for g in range(G)])
+    _close(kmax, want, 1e-4, "max |k|^2 per (group, head)")
+    assert (kmax * 1.004 ** 2 >= (k.float() ** 2).sum(-1).amax(-1)).all(), "must bound the norms of the stored bf16 rows"
+
+
 def test_gemm_qkv_window_partition_on_store():
     """The windowed blocks' QKV projection (image_encoder.py:168-172, 227-229): the reference zero-pads the normalised
     64x64 map to 70x70, partitions it into 25 windows of 14x14 and projects all 4900 tokens per image.  Here the GEMM runs

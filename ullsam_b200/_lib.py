@@ -87,6 +87,7 @@ class GemmDesc(C.Structure):
         ("row_stats", C.c_void_p),
         ("fold_s", C.c_void_p),
         ("pad_bias", C.c_void_p),
+        ("kmax_sq", C.c_void_p),
     ]
 
 

@@ -57,7 +57,7 @@ int ullsam_op_gemm(const ullsam_gemm_desc* d, void* stream) {
   p.T = d->T; p.heads = d->heads;
   p.ln_w = d->ln_w; p.ln_b = d->ln_b; p.ln_eps = d->ln_eps; p.hw = d->hw;
   p.out2 = d->out2; p.ln_partition = d->ln_partition;
-  p.row_stats = d->row_stats; p.fold_s = d->fold_s; p.pad_bias = d->pad_bias;
+  p.row_stats = d->row_stats; p.fold_s = d->fold_s; p.pad_bias = d->pad_bias; p.kmax_sq = d->kmax_sq;
   const char* e = launch_gemm(d->epi, d->A, d->W, p, sms, static_cast<cudaStream_t>(stream));
   return e ? op_fail(ULLSAM_ERR_CUDA, e) : ULLSAM_OK;
 }

@@ -359,8 +359,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #endif
         if (leader) {
 #pragma unroll
-          for (int s2 = 0; s2 < BN / 16; ++s2)
-            umma_ts(t_o, t_slot + s2 * 8, dv + s2 * 128, idesc_pv, (j | s2) != 0);
+          for (int s2 = 0; s2 < BN / 16; ++s2) {
+            // P(keys 16 s2 .. + 15) as 8 packed columns.  One thread per row: contiguous.  Two threads per row (global):
+            // every 32-key quarter of the tile sits at the START of the 32 score columns its thread read it from
+            // (key-grid row s2 / 4, column half (s2 / 2) & 1), so no thread ever writes columns the other one still reads.
+            const uint32_t pcol = (A::GLOBAL && A::SPLIT == 2) ? (s2 >> 2) * 64 + ((s2 >> 1) & 1) * 32 + (s2 & 1) * 8 : s2 * 8;
+            umma_ts(t_o, t_slot + pcol, dv + s2 * 128, idesc_pv, (j | s2) != 0);
+          }
           umma_commit(bar_o);
           if (qt == QT - 1) umma_commit(&v_empty[vstage]);
           if (has_qk) {
@@ -440,7 +445,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             qq = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, qq));
           }
         }
-        qnorm_k = sqrtf(qq) * kmaxv;
+        qnorm_k = sqrtf(qq * kmaxv) * 1.004f;   // kmaxv = max |k|^2, possibly of the fp32 values before their bf16 rounding (+0.4 %)
       }
       mbar_wait(pro_mma_done, 0);
       tc_fence_after();
@@ -767,9 +772,42 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float m_used = -INFINITY;          // reference point of the exponentials (log2 units), identical in the pair
     float l = 0.f;                     // partial row sum (this thread's columns)
     const uint32_t o_addr = lane_addr + A::COL_O + qt * 64 + hs * 32;  // this thread's 32 of the 64 O columns
+    // Global grid, fast mode (the a-priori bound of the one-thread-per-row path): once the reference point chosen on the
+    // first tile is within 2^100 of an upper bound of EVERY biased score of the row, nothing can overflow any more, the
+    // reference point never moves again and the two threads of a row have nothing left to exchange: each exponentiates
+    // its 2 x 32 scores of a tile (its 32 rel_w values live in registers) and hands its half of P over.  Four softmax
+    // warps per sub-partition instead of two, at the same instruction count per element.
+    float bound_rest = INFINITY;
+    bool fast = false;
+    if constexpr (A::GLOBAL) {
+      float wmax = -INFINITY, hmax = -INFINITY;
+#pragma unroll
+      for (int k4 = 0; k4 < 16; ++k4) {
+        const float4 w = *reinterpret_cast<const float4*>(relw_s + (k4 * NROWS + tidq) * 4);
+        wmax = fmaxf(fmaxf(wmax, fmaxf(w.x, w.y)), fmaxf(w.z, w.w));
+      }
+#pragma unroll 8
+      for (int kh = 0; kh < 64; ++kh) hmax = fmaxf(hmax, __half2float(relh_s[kh * NROWS + tidq]));
+      if (kmax_norm != nullptr) {
+        const uint8_t* qrow = smem + A::OFF_Q + qt * A::QBYTES + r * 128;   // 128-byte swizzle: 16-byte chunk c at c ^ (r & 7)
+        float qq = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = *reinterpret_cast<const uint4*>(qrow + ((c ^ (r & 7)) << 4));
+          const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f2 = __bfloat1622float2(b2[e]);
+            qq = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, qq));
+          }
+        }
+        bound_rest = fmaf(sqrtf(qq * __ldg(kmax_norm + gh)) * 1.004f, cs, wmax + hmax) + 0.0625f;
+      }
+    }
 
+    int j = 0;
 #pragma unroll 1
-    for (int j = 0; j < NT; ++j) {
+    for (; j < NT && !fast; ++j) {
       const int n = j * QT + qt;
       const uint32_t s_addr = lane_addr + (n % NSLOT) * 128;
       mbar_wait(&s_full[n % NSLOT], (n / NSLOT) & 1);
@@ -870,9 +908,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           v[1][i >> 1] = pack_bf16(p2, p3);
         }
         l += ls0 + ls1;
-        // keys hs*32.. -> packed columns hs*16..; keys 64+hs*32.. -> packed columns 32+hs*16..
-        tmem_st16(s_addr + hs * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[0][0]));
-        tmem_st16(s_addr + 32 + hs * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[1][0]));
+        // keys hs*32.. -> 16 packed columns at hs*32; keys 64+hs*32.. -> 16 packed columns at 64+hs*32 (the layout the MMA
+        // warp reads, see the PV issue; here every score of the row was read before the exchange barrier above)
+        tmem_st16(s_addr + hs * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0][0]));
+        tmem_st16(s_addr + 64 + hs * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[1][0]));
+        // fast mode from the next tile on?  The answer has to be the same in all eight warps of the query tile (the slow
+        // path meets at a named barrier every tile): a barrier with an AND reduction.
+        {
+          const int ok = bound_rest <= m_used + 100.0f;
+          int all_ok;
+          asm volatile(
+              "{\n\t"
+              ".reg .pred p, q;\n\t"
+              "setp.ne.b32 q, %2, 0;\n\t"
+              "barrier.cta.red.and.pred p, %1, 256, q;\n\t"
+              "selp.b32 %0, 1, 0, p;\n\t"
+              "}\n"
+              : "=r"(all_ok)
+              : "r"(bar_id), "r"(ok)
+              : "memory");
+          fast = all_ok != 0;
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < HALF; i += 2) {
@@ -895,6 +951,55 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[qt]);
+    }
+
+    if constexpr (A::GLOBAL) {
+      // ---- fast mode: the rest of the tiles (a separate loop, so the 32 rel_w registers are not live in the slow one) ----
+      float wreg[32];
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const float4 w = *reinterpret_cast<const float4*>(relw_s + ((hs * 8 + k4) * NROWS + tidq) * 4);
+        wreg[k4 * 4] = w.x; wreg[k4 * 4 + 1] = w.y; wreg[k4 * 4 + 2] = w.z; wreg[k4 * 4 + 3] = w.w;
+      }
+#pragma unroll 1
+      for (; j < NT; ++j) {
+        const int n = j * QT + qt;
+        const uint32_t s_addr = lane_addr + (n % NSLOT) * 128;
+        mbar_wait(&s_full[n % NSLOT], (n / NSLOT) & 1);
+        tc_fence_after();
+        // pieces of 16 scores: piece p = key-grid row p / 2, columns hs * 32 + (p & 1) * 16 .. + 15; its 8 packed P columns
+        // go to the start of the same 32-column block (already consumed: the block's two pieces are read in order)
+        const float c0 = __half2float(relh_s[(2 * j) * NROWS + tidq]) - m_used;
+        const float c1 = __half2float(relh_s[(2 * j + 1) * NROWS + tidq]) - m_used;
+        uint32_t pb[2][16];
+        float la = 0.f, lb = 0.f;
+        tmem_ld16(s_addr + hs * 32, pb[0]);
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc) {
+          const uint32_t blk = s_addr + (pc >> 1) * 64 + hs * 32;
+          tmem_wait_ld();
+          if (pc + 1 < 4) tmem_ld16(s_addr + ((pc + 1) >> 1) * 64 + hs * 32 + ((pc + 1) & 1) * 16, pb[(pc + 1) & 1]);
+          const float cc = (pc >> 1) ? c1 : c0;
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float x0 = fmaf(__uint_as_float(pb[pc & 1][i]), cs, cc) + wreg[(pc & 1) * 16 + i];
+            const float x1 = fmaf(__uint_as_float(pb[pc & 1][i + 1]), cs, cc) + wreg[(pc & 1) * 16 + i + 1];
+            const float p0 = ex2(x0), p1 = ex2(x1);
+            la += p0;
+            lb += p1;
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st8(blk + (pc & 1) * 8, pk);
+        }
+        l += la + lb;
+        tmem_wait_st();
+        // hand-over back-pressure (see the one-thread-per-row path): P(j) only after the MMA warp has observed P(j-1)
+        if (j > 0) mbar_wait(&o_done[qt * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[qt]);
+      }
     }
 
     // ------------------------------------ epilogue: O / l -> out ---------------------------------------
@@ -982,7 +1087,7 @@ __global__ void __launch_bounds__(256) k_norm_max_kernel(const __nv_bfloat16* __
     float m = red[0];
 #pragma unroll
     for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
-    out[blockIdx.x] = sqrtf(m);
+    out[blockIdx.x] = m;   // squared, like the QKV epilogue's running maximum (GemmParams::kmax_sq)
   }
 }
 
@@ -1010,7 +1115,7 @@ const char* launch_t(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
 
 const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
                              const __nv_bfloat16* rel_h, const __nv_bfloat16* rel_w, int G, int heads, int grid,
-                             __nv_bfloat16* out, cudaStream_t stream, float* kmax_scratch) {
+                             __nv_bfloat16* out, cudaStream_t stream, float* kmax_scratch, bool kmax_valid) {
   if (G <= 0) return nullptr;
   if (grid == 64) {
     // pre-pass: max key norm per (image, head) for the a-priori score bound (see the kernel); scratch of G * heads floats
@@ -1018,7 +1123,8 @@ const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, con
     float* kmax = kmax_scratch;
     if (kmax == nullptr && cudaMallocAsync(&kmax, static_cast<size_t>(G) * heads * sizeof(float), stream) != cudaSuccess)
       return "attention: cudaMallocAsync failed";
-    if (launch_pdl(k_norm_max_kernel, dim3(G * heads), dim3(256), 0, stream, 1, k, 4096, kmax) != cudaSuccess)
+    if (kmax_valid && kmax_scratch == nullptr) return "attention: kmax_valid without a kmax buffer";
+    if (!kmax_valid && launch_pdl(k_norm_max_kernel, dim3(G * heads), dim3(256), 0, stream, 1, k, 4096, kmax) != cudaSuccess)
       return "attention: key-norm pre-pass launch failed";
     const char* e = launch_t<64>(q, k, v, rel_h, rel_w, G, heads, kmax, out, stream);
     if (kmax_scratch == nullptr) cudaFreeAsync(kmax, stream);

@@ -13,7 +13,9 @@ namespace ullsam {
 // rows are dropped on the store (image_encoder.py:224-289, 325-361).
 const char* launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
                              const __nv_bfloat16* rel_h, const __nv_bfloat16* rel_w, int G, int heads, int grid, __nv_bfloat16* out, cudaStream_t stream,
-                             float* kmax_scratch = nullptr /* grid 64: G * heads floats (else allocated stream-ordered) */);
+                             float* kmax_sq = nullptr /* grid 64: G * heads floats (else allocated stream-ordered) */,
+                             bool kmax_valid = false /* kmax_sq already holds max_t |k[g][head][t]|^2 (written by the QKV GEMM's
+                                                        epilogue, GemmParams::kmax_sq): the pre-pass over K is skipped */);
 
 // second windowed design (attention_win.cu): one CTA per (window, head), both query tiles, 7 key tiles of 28
 const char* launch_attention_windowed_v2(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,

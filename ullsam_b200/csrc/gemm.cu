@@ -93,6 +93,8 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
     return "gemm: the folded-LayerNorm epilogues need N % 256 == 0, K % 256 == 0, K <= 1024, bias, fold_s and row_stats";
   if (epi == EPI_QKV_FOLD && p.ln_partition && !p.pad_bias) return "gemm: EPI_QKV_FOLD with window scatter needs pad_bias";
   if (epi == EPI_RES_STATS && !p.residual) return "gemm: EPI_RES_STATS needs residual";
+  if (p.kmax_sq != nullptr && (p.T % 32 != 0 || p.ln_partition || p.heads % 2 != 0))
+    return "gemm: kmax_sq needs T % 32 == 0, rows in group order and an even number of heads";
   if (p.K % GEMM_BK != 0) return "gemm: K must be a multiple of 64";
   const bool ln = (epi == EPI_LN_BF16 || epi == EPI_LN_NCHW || epi == EPI_LN_RES || epi == EPI_UP1);
   int bn = (p.N % 256 == 0) ? 256 : 128;
@@ -120,7 +122,7 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
   const bool pair = (epi == EPI_RES_LN) ||
                     (!pair_disabled && bn == 256 && !p.a_conv3 && p.M >= 4096 &&
                      (epi == EPI_BF16 || epi == EPI_GELU_BF16 || epi == EPI_RES_F32 || epi == EPI_QKV || epi == EPI_RES_STATS ||
-                      epi == EPI_QKV_FOLD || epi == EPI_GELU_FOLD));
+                      epi == EPI_QKV_FOLD || epi == EPI_GELU_FOLD || epi == EPI_PATCH || epi == EPI_PATCH_STATS));
   e = make_tmap_2d_bf16(&tb, W, (uint64_t)p.N, (uint64_t)p.K, pair ? 128 : bn, GEMM_BK);
   if (e) return e;
   if (pair) {
@@ -135,6 +137,8 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
                           : launch_pair<EPI_RES_F32, 8>(ta, tb, p, num_sms, stream);
       case EPI_RES_LN: return launch_pair<EPI_RES_LN, 8>(ta, tb, p, num_sms, stream);
       case EPI_RES_STATS: return launch_pair<EPI_RES_STATS, 8>(ta, tb, p, num_sms, stream);
+      case EPI_PATCH: return launch_pair<EPI_PATCH, 8>(ta, tb, p, num_sms, stream);
+      case EPI_PATCH_STATS: return launch_pair<EPI_PATCH_STATS, 8>(ta, tb, p, num_sms, stream);
       case EPI_QKV_FOLD: return launch_pair<EPI_QKV_FOLD, 8>(ta, tb, p, num_sms, stream);
       case EPI_GELU_FOLD:
         return (ew16 & 1) ? launch_pair<EPI_GELU_FOLD, 16>(ta, tb, p, num_sms, stream)

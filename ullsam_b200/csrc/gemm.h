@@ -77,6 +77,9 @@ struct GemmParams {
   float* row_stats;       // EPI_*_STATS (written) / EPI_*_FOLD (read): [M][kStatSlots] pairs (sum, sum of squares)
   const float* fold_s;    // EPI_*_FOLD: [N] column sums of the bf16 weight gamma*W
   const float* pad_bias;  // EPI_QKV_FOLD with ln_partition: [N] bias of the projection itself
+  float* kmax_sq;         // EPI_QKV / EPI_QKV_FOLD, optional: [M / T][heads] running maximum of |k row|^2 per (group, head),
+                          // the key-norm bound the global attention uses (attention.h) — folded with atomicMax on the float
+                          // bits (non-negative values), so the caller zeroes it first; T must be a multiple of 32
 };
 
 constexpr int kStatSlots = 8;  // 128-column slices per row the statistics buffer has room for (LayerNorm dim <= 1024)

@@ -666,6 +666,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
 #endif
         const int rr = lane >> 2, cc = lane & 3;  // transposed phase: row-in-group, 16-byte column slot
+        float ksq = 0.f;                          // EPI_QKV with kmax_sq: |k row|^2 of the first chunk of a head
         size_t qkv_row_off[4] = {0, 0, 0, 0};     // EPI_QKV: (g * heads * T + t) * 64 of the 4 rows this lane stores
         if constexpr (kIsQkv) {
 #pragma unroll
@@ -835,6 +836,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             } else if (p.act == ACT_RELU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+          }
+          if constexpr (kIsQkv) {
+            // key-norm bound for the global attention: max over the warp's 32 rows of |k row|^2, one head = two chunks
+            if (p.kmax_sq != nullptr) {
+              const int dim = p.heads * 64;
+              if (n0 >= dim && n0 < 2 * dim) {          // (warp-uniform: a chunk lies inside one of q / k / v)
+                float sq = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sq = fmaf(f[j], f[j], sq);
+                ksq = (c & 1) ? ksq + sq : sq;
+                if (c & 1) {
+                  const float m = warp_max(row_ok ? ksq : 0.f);
+                  if (lane == 0 && tile_row0 < p.M)
+                    atomicMax(reinterpret_cast<int*>(p.kmax_sq) + (tile_row0 / p.T) * p.heads + ((n0 - dim) >> 6), __float_as_int(m));
+                }
+              }
             }
           }
           if constexpr (EPI == EPI_BF16 || kIsGelu || kIsQkv) {

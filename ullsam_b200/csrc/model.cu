@@ -231,6 +231,12 @@ int weights_fence(ullsam_handle* h, cudaStream_t st) {
   return ULLSAM_OK;
 }
 
+// "is this environment switch set to 0?"
+bool getenv_off(const char* name) {
+  const char* v = getenv(name);
+  return v != nullptr && atoi(v) == 0;
+}
+
 template <typename T>
 T* dalloc(ullsam_handle* h, size_t count, bool zero = false) {
   void* p = nullptr;
@@ -612,6 +618,8 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
   // embedding, attn.proj, mlp.lin2) also writes its bf16 copy and per-row partial sums, and attn.qkv / mlp.lin1 run on that
   // copy with gamma-scaled weights and finish the normalisation in their epilogue — no LayerNorm kernel, no cast before
   // the neck.  (D % 256 == 0 and D <= 1024: ViT-B and ViT-L.)
+  // ULLSAM_KMAX_EPI=0: the global attention takes its key-norm bound from a pre-pass over K instead of the QKV epilogue
+  static const bool kmax_epi = !getenv_off("ULLSAM_KMAX_EPI");
   const bool foldable = D % 256 == 0 && D <= 128 * kStatSlots;
   const bool fold1 = foldable && (h->ln_fold & 1), fold2 = foldable && (h->ln_fold & 2);
   if (fold1 || fold2)
@@ -652,12 +660,17 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
       if (fold1) {
         p.bias = b.qkv_c; p.fold_s = b.qkv_s; p.pad_bias = b.qkv_b; p.row_stats = h->row_stats; p.ln_eps = c.enc_ln_eps;
       }
+      if (b.global && kmax_epi) {   // max |k|^2 per (image, head) for the global attention's score bound rides on this epilogue
+        CKC(cudaMemsetAsync(h->kmax, 0, static_cast<size_t>(Bc) * heads * sizeof(float), st));
+        p.kmax_sq = h->kmax;
+      }
       CKS(launch_gemm(fold1 ? EPI_QKV_FOLD : EPI_QKV, h->xn_t, fold1 ? b.qkv_wf : b.qkv_w, p, sms, st));
       mark(h, PC_GEMM_QKV, st);
     }
     // attention (+ rel-pos bias, + window_unpartition)
-    CKS(launch_attention(h->q, h->k, h->v, b.relh, b.relw, b.global ? Bc : Bc * 25, heads, b.global ? 64 : 14, h->ao, st, h->kmax));
-    mark(h, b.global ? PC_ATTN_GLOBAL : PC_ATTN_WIN, st, b.global ? 2 : 1);  // (global: key-norm pre-pass + attention)
+    CKS(launch_attention(h->q, h->k, h->v, b.relh, b.relw, b.global ? Bc : Bc * 25, heads, b.global ? 64 : 14, h->ao, st, h->kmax,
+                         b.global && kmax_epi));
+    mark(h, b.global ? PC_ATTN_GLOBAL : PC_ATTN_WIN, st, (b.global && !kmax_epi) ? 2 : 1);  // (+ the key-norm pre-pass)
     {  // proj + residual (+ norm2)
       GemmParams p = gp(tok, D, D);
       p.bias = b.proj_b; p.out = h->x; p.residual = h->x;

@@ -66,9 +66,10 @@ def gemm(
     row_stats: Optional[torch.Tensor] = None,
     fold_s: Optional[torch.Tensor] = None,
     pad_bias: Optional[torch.Tensor] = None,
+    kmax_sq: Optional[torch.Tensor] = None,
 ) -> Optional[torch.Tensor]:
     """C = A[M,K] @ W[N,K]^T with the epilogue selected by ``epi`` (see include/ullsam.h)."""
-    _require_cuda(a, w, bias, out, residual, pos, ln_w, ln_b, out2, row_stats, fold_s, pad_bias)
+    _require_cuda(a, w, bias, out, residual, pos, ln_w, ln_b, out2, row_stats, fold_s, pad_bias, kmax_sq)
     if row_stats is not None:  # fp32 [M, STAT_SLOTS, 2]: (sum, sum of squares) per row and 128-column slice
         assert row_stats.dtype == torch.float32 and row_stats.is_contiguous() and row_stats.numel() == a.shape[0] * _lib.STAT_SLOTS * 2
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
@@ -104,7 +105,7 @@ def gemm(
     d.pos_rows = pos.shape[0] if pos is not None else 0
     d.ln_w, d.ln_b, d.ln_eps, d.hw = ptr(ln_w), ptr(ln_b), ln_eps, hw
     d.out2, d.ln_partition = ptr(out2), int(ln_partition)
-    d.row_stats, d.fold_s, d.pad_bias = ptr(row_stats), ptr(fold_s), ptr(pad_bias)
+    d.row_stats, d.fold_s, d.pad_bias, d.kmax_sq = ptr(row_stats), ptr(fold_s), ptr(pad_bias), ptr(kmax_sq)
     check(_lib.load().ullsam_op_gemm(C.byref(d), current_stream_ptr(a.device)), what="ullsam_op_gemm")
     return out
 
