@@ -516,7 +516,7 @@ def main():
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             e2e["c_abi_host"] = {"value": world * B * args.steps / dt.item(), "unit": "images/s",
-                                 "api": "ullsam_segment_host: one synchronous call per step, sub-batches of 8 pipelined on "
+                                 "api": "ullsam_segment_host: one synchronous call per step, sub-batches of 4 / 12 / 16 images pipelined on "
                                         "two internal streams (no gather)"}
             barrier()
 

@@ -129,7 +129,7 @@ int ullsam_transformer_forward(ullsam_handle* h, const void* image_embedding, in
 
 /* End-to-end with HOST buffers (pinned recommended; pageable works but its copies are staged and serial): H2D of the
  * images and prompts, encoder, decoder (one prompt set per image), D2H of masks / iou / optionally embeddings;
- * synchronises before returning.  Internally the batch is cut into sub-batches of 8 images on two private streams so
+ * synchronises before returning.  Internally the batch is cut into growing sub-batches (4, 12, 16 images of every 32) on two private streams so
  * the H2D copy of sub-batch i+1 and the D2H copy of sub-batch i-1 overlap the kernels of sub-batch i.
  * bench.py reports this call as `e2e.c_abi_host` (one synchronous call per step); its headline `e2e` figure is measured
  * one level up, through the Python Engine API with pinned host tensors, where copies also overlap ACROSS steps. */

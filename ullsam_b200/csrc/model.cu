@@ -1237,8 +1237,11 @@ int ullsam_segment_host(ullsam_handle* h, const float* images_host, int B, const
   if (int rc = ensure_encoder_ws(h, B < kEncChunk ? B : kEncChunk)) return rc;
   // Two internal streams: the copy stream moves sub-batch i+1 of the images to the device (and results back) while the
   // compute stream runs encoder + decoder on sub-batch i, so only the first sub-batch's H2D and the last one's D2H are
-  // exposed (pinned host buffers; pageable memory degrades to staged, serial copies).
-  constexpr int kSub = 8, kMaxSub = kEncChunk / kSub;
+  // exposed (pinned host buffers; pageable memory degrades to staged, serial copies).  The sub-batches grow — 4, 12, 16
+  // images of a 32-image chunk: a small first one so that compute starts after 50 MB of copies instead of 100, large later
+  // ones because the GEMMs run below their best on 8-image batches.
+  constexpr int kMaxSub = 4;
+  static const int kSubSizes[kMaxSub] = {4, 12, 16, kEncChunk};
   if (!h->hs_copy) {
     CKC(cudaStreamCreateWithFlags(&h->hs_copy, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&h->hs_comp, cudaStreamNonBlocking));
@@ -1255,15 +1258,20 @@ int ullsam_segment_host(ullsam_handle* h, const float* images_host, int B, const
   CKC(cudaMemcpyAsync(h->d_dense, dense_vec_host, 256 * 4, cudaMemcpyHostToDevice, cs));
   for (int c0 = 0; c0 < B; c0 += kEncChunk) {          // outer chunk: what the embedding staging buffer holds
     const int Bo = (B - c0 < kEncChunk) ? (B - c0) : kEncChunk;
-    const int nsub = (Bo + kSub - 1) / kSub;
+    int nsub = 0, sub_off[kMaxSub + 1] = {0};
+    while (sub_off[nsub] < Bo && nsub < kMaxSub) {
+      const int left = Bo - sub_off[nsub];
+      sub_off[nsub + 1] = sub_off[nsub] + (kSubSizes[nsub] < left ? kSubSizes[nsub] : left);
+      ++nsub;
+    }
     for (int i = 0; i < nsub; ++i) {
-      const int b0 = c0 + i * kSub, Bc = (Bo - i * kSub < kSub) ? (Bo - i * kSub) : kSub;
+      const int b0 = c0 + sub_off[i], Bc = sub_off[i + 1] - sub_off[i];
       CKC(cudaMemcpyAsync(h->d_images + b0 * img, images_host + b0 * img, Bc * img * 4, cudaMemcpyHostToDevice, cs));
       CKC(cudaEventRecord(h->hs_ev[i], cs));
     }
     for (int i = 0; i < nsub; ++i) {
-      const int b0 = c0 + i * kSub, Bc = (Bo - i * kSub < kSub) ? (Bo - i * kSub) : kSub;
-      float* emb = h->emb_f32 + static_cast<size_t>(i * kSub) * embn;
+      const int b0 = c0 + sub_off[i], Bc = sub_off[i + 1] - sub_off[i];
+      float* emb = h->emb_f32 + static_cast<size_t>(sub_off[i]) * embn;
       CKC(cudaStreamWaitEvent(ks, h->hs_ev[i], 0));
       if (int rc = encoder_chunk(h, h->d_images + b0 * img, ULLSAM_F32, Bc, emb, ks)) return rc;
       if (int rc = decoder_run(h, emb, Bc, h->d_pe, h->d_sparse + static_cast<size_t>(b0) * Ns * 256, 1, Ns, h->d_dense, 1, 1,
@@ -1273,14 +1281,14 @@ int ullsam_segment_host(ullsam_handle* h, const float* images_host, int B, const
       CKC(cudaEventRecord(h->hs_ev[kMaxSub + i], ks));
     }
     for (int i = 0; i < nsub; ++i) {
-      const int b0 = c0 + i * kSub, Bc = (Bo - i * kSub < kSub) ? (Bo - i * kSub) : kSub;
+      const int b0 = c0 + sub_off[i], Bc = sub_off[i + 1] - sub_off[i];
       CKC(cudaStreamWaitEvent(cs, h->hs_ev[kMaxSub + i], 0));
       CKC(cudaMemcpyAsync(masks_host + static_cast<size_t>(b0) * cnt * 65536, h->d_masks + static_cast<size_t>(b0) * cnt * 65536,
                           static_cast<size_t>(Bc) * cnt * 65536 * 4, cudaMemcpyDeviceToHost, cs));
       CKC(cudaMemcpyAsync(iou_host + static_cast<size_t>(b0) * cnt, h->d_iou + static_cast<size_t>(b0) * cnt,
                           static_cast<size_t>(Bc) * cnt * 4, cudaMemcpyDeviceToHost, cs));
       if (emb_host)
-        CKC(cudaMemcpyAsync(emb_host + static_cast<size_t>(b0) * embn, h->emb_f32 + static_cast<size_t>(i * kSub) * embn,
+        CKC(cudaMemcpyAsync(emb_host + static_cast<size_t>(b0) * embn, h->emb_f32 + static_cast<size_t>(sub_off[i]) * embn,
                             static_cast<size_t>(Bc) * embn * 4, cudaMemcpyDeviceToHost, cs));
     }
     // (the next outer chunk's H2D copies queue behind these D2H copies on the copy stream, and its compute waits for
