@@ -162,7 +162,8 @@ typedef struct {
                  * 12 epi 1, plus out2 = bf16(out) and row_stats[row][2 * (n / 256) + (n % 256) / 128] = (sum, sum of squares)
                  *    of the row's 128-column slice | 13 epi 3 with the same two extra outputs
                  * 14 epi 2 on the un-normalised rows: W = bf16(gamma*W), bias = c, fold_s = s, mean / rstd from row_stats
-                 *    (K / 128 slices), pad_bias = b | 15 epi 0 + GELU(erf), same */
+                 *    (K / 128 slices), pad_bias = b | 15 epi 0 + GELU(erf), same
+                 * 16 epi 1 with out == residual (in place), the add performed by the memory system (TMA reduce-add stores) */
   int32_t M, N, K;
   int32_t a_conv3, conv_c;
   const void* A;     /* bf16 */

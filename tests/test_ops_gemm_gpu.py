@@ -58,6 +58,24 @@ def test_gemm_residual_inplace():
     _close(x, ref, 1e-4, "residual")
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 768, 768), (2 * 4096 + 300, 1024, 1024), (4096 + 17, 768, 3072)])
+def test_gemm_residual_by_tma_reduce_add(M, N, K):
+    """EPI_RES_RED: x += A W^T + b with the add done by TMA reduce-add stores (the residual stream never enters the SM).
+    Same two roundings as EPI_RES_F32 (fp32(acc + b), then + x), so the two must agree bit for bit; rows beyond M of the
+    last 32-row box are clipped by the tensor map."""
+    from ullsam_b200 import _lib, ops
+
+    a, w, b = _mk(M, N, K, 31)
+    res = torch.randn(M + 64, N, device="cuda")          # 64 guard rows behind the matrix: must stay untouched
+    x, y = res.clone(), res.clone()
+    ops.gemm(a, w, b, epi=_lib.EPI_RES_RED, out=x[:M], residual=x[:M])
+    ops.gemm(a, w, b, epi=_lib.EPI_RES_F32, out=y[:M], residual=y[:M])
+    torch.cuda.synchronize()
+    _close(x[:M], _ref(a, w, b) + res[:M], 1e-4, f"res_red {M}x{N}x{K}")
+    assert torch.equal(x[M:], res[M:]), "rows behind the matrix were written"
+    assert torch.equal(x[:M], y[:M]), "reduce-add and in-SM add must agree bit for bit"
+
+
 @pytest.mark.parametrize("partition", [False, True])
 @pytest.mark.parametrize("K", [768, 3072])
 def test_gemm_residual_with_fused_layernorm(K, partition):

@@ -19,6 +19,7 @@ F32, BF16, F16 = 0, 1, 2
 EPI_BF16, EPI_RES_F32, EPI_QKV, EPI_PATCH, EPI_LN_BF16, EPI_LN_NCHW, EPI_F32 = range(7)
 EPI_LN_RES = 7   # x = acc + bias + residual; LayerNorm(256) -> out fp32 (may alias residual) and out2 bf16 (decoder norm4)
 EPI_RES_STATS, EPI_PATCH_STATS, EPI_QKV_FOLD, EPI_GELU_FOLD = 12, 13, 14, 15  # LayerNorm folded into the GEMMs around it
+EPI_RES_RED = 16  # EPI_RES_F32 in place, the add done by TMA reduce-add stores
 STAT_SLOTS = 8   # 128-column slices per row of the row_stats buffer
 EPI_RES_LN = 11  # +residual fp32 and the LayerNorm that follows it -> bf16 (optionally window-partitioned)
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2

@@ -169,6 +169,19 @@ ULLSAM_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* b
       : "memory");
 }
 
+// TMA store with an fp32 add performed at the memory side (global[tile] += smem[tile]); bulk-group completion
+ULLSAM_DEVICE void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+ULLSAM_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+ULLSAM_DEVICE void tma_store_wait_read() {   // all but the N most recent bulk groups have finished READING shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+ULLSAM_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 ULLSAM_DEVICE void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
                                int c3) {
   asm volatile(

@@ -42,6 +42,19 @@ const char* make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows,
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(2d) failed";
 }
 
+const char* make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                             uint32_t box_cols) {
+  if (const char* e = load_encode()) return e;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(2d fp32) failed";
+}
+
 const char* make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t box_c,
                                 uint32_t box_w, uint32_t box_h) {
   if (const char* e = load_encode()) return e;
@@ -58,14 +71,14 @@ const char* make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, int B, int H
 // CTA-pair variant: cluster (2,1,1), one pair per 256 x 256 tile
 template <int EPI, int EW>
 static const char* launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
-                               cudaStream_t stream) {
-  using L = GemmSmem<256, 2, EW>;
+                               cudaStream_t stream, const CUtensorMap* tc = nullptr) {
+  using L = GemmSmem<256, 2, EW, EPI == EPI_RES_RED>;
   static PerDeviceOnce configured;
   auto kern = gemm_kernel<256, EPI, 2, EW>;
   if (const char* ce = set_max_smem_once(configured, kern, L::kTotal)) return ce;
   const int tiles = ((p.M + 255) / 256) * (p.N / 256);
   const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
-  cudaError_t e = launch_pdl(kern, dim3(2 * pairs), dim3((GEMM_EPI_WARP0 + EW) * 32), L::kTotal, stream, 2, ta, tb, p);
+  cudaError_t e = launch_pdl(kern, dim3(2 * pairs), dim3((GEMM_EPI_WARP0 + EW) * 32), L::kTotal, stream, 2, ta, tb, tc ? *tc : ta, p);
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -78,7 +91,7 @@ static const char* launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const 
   if (const char* ce = set_max_smem_once(configured, kern, L::kTotal)) return ce;
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * (p.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::kTotal, stream, 1, ta, tb, p);
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), L::kTotal, stream, 1, ta, tb, ta, p);
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -93,6 +106,8 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
     return "gemm: the folded-LayerNorm epilogues need N % 256 == 0, K % 256 == 0, K <= 1024, bias, fold_s and row_stats";
   if (epi == EPI_QKV_FOLD && p.ln_partition && !p.pad_bias) return "gemm: EPI_QKV_FOLD with window scatter needs pad_bias";
   if (epi == EPI_RES_STATS && !p.residual) return "gemm: EPI_RES_STATS needs residual";
+  if (epi == EPI_RES_RED && (p.N % 256 != 0 || p.a_conv3 || p.M < 4096 || p.residual != p.out || p.ldc != p.N || !p.out))
+    return "gemm: EPI_RES_RED needs N % 256 == 0, M >= 4096, a plain A matrix and out == residual (in place, ldc == N)";
   if (p.kmax_sq != nullptr && (p.T % 32 != 0 || p.ln_partition || p.heads % 2 != 0))
     return "gemm: kmax_sq needs T % 32 == 0, rows in group order and an even number of heads";
   if (p.K % GEMM_BK != 0) return "gemm: K must be a multiple of 64";
@@ -119,6 +134,12 @@ const char* launch_gemm(int epi, const void* A, const void* W, const GemmParams&
   }
   if ((epi == EPI_QKV || epi == EPI_QKV_FOLD) && p.ln_partition && (p.M % 4096 != 0 || p.T != 196))
     return "gemm: EPI_QKV window scatter needs whole 64x64 token grids and T == 196";
+  if (epi == EPI_RES_RED) {
+    CUtensorMap tc;
+    if ((e = make_tmap_2d_bf16(&tb, W, (uint64_t)p.N, (uint64_t)p.K, 128, GEMM_BK))) return e;
+    if ((e = make_tmap_2d_f32(&tc, p.out, (uint64_t)p.M, (uint64_t)p.N, 32, 32))) return e;
+    return launch_pair<EPI_RES_RED, 8>(ta, tb, p, num_sms, stream, &tc);
+  }
   const bool pair = (epi == EPI_RES_LN) ||
                     (!pair_disabled && bn == 256 && !p.a_conv3 && p.M >= 4096 &&
                      (epi == EPI_BF16 || epi == EPI_GELU_BF16 || epi == EPI_RES_F32 || epi == EPI_QKV || epi == EPI_RES_STATS ||

@@ -40,6 +40,10 @@ enum EpiMode : int {
                          // of a row from the K / 128 partial sums in row_stats; pad_bias = the projection's own bias
                          // (k / v rows of the window-padding tokens)
   EPI_GELU_FOLD = 15,    // EPI_GELU_BF16, same
+  EPI_RES_RED = 16,      // EPI_RES_F32 with out == residual, the add done by the memory system: the epilogue stages acc + bias
+                         // in shared memory (32 x 32 fp32 boxes, 128-byte swizzle) and issues TMA reduce-add stores
+                         // (cp.reduce.async.bulk.tensor ... .add) — the residual stream is never read into the SM, so the
+                         // epilogue does not wait for DRAM at all.  Bit-identical to EPI_RES_F32 (same two roundings).
 };
 // EPI_BF16 / EPI_F32 also add pos[row % pos_rows][n] when p.pos != nullptr.
 
@@ -87,6 +91,9 @@ constexpr int kStatSlots = 8;  // 128-column slices per row the statistics buffe
 // All return nullptr on success or a static error string.
 const char* make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                               uint32_t box_cols);
+// fp32 [rows, cols] row-major, 128-byte swizzle (box_cols * 4 <= 128)
+const char* make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                             uint32_t box_cols);
 const char* make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t box_c,
                                 uint32_t box_w, uint32_t box_h);
 // A: bf16 [M,K] row-major (or NHWC [B,64,64,C] when p.a_conv3); W: bf16 [N,K] row-major.

@@ -70,9 +70,11 @@ constexpr int GEMM_EPI_WARP0 = 4;
 // each CTA stages its own 128 rows of A and its own BN/2 rows of W, the leader issues one 256 x BN x 16 MMA that
 // reads both CTAs' shared memory, and each CTA's TMEM receives its 128 accumulator rows.  Halving the per-CTA W
 // traffic is what lifts the shared-memory / L2 operand-feed bound of the single-CTA kernel.
-template <int BN, int CG = 1, int EW = 8>
+// RED: the TMA reduce-add epilogue (EPI_RES_RED) — two 4 KB staging boxes per epilogue warp, paid for with two pipeline
+// stages (its K = 768 main loop has 12 k-blocks; four stages cover it).
+template <int BN, int CG = 1, int EW = 8, bool RED = false>
 struct GemmSmem {
-  static constexpr int kStages = (BN == 256 && CG == 1) ? 4 : (EW == 16 ? 5 : 6);
+  static constexpr int kStages = RED ? 4 : ((BN == 256 && CG == 1) ? 4 : (EW == 16 ? 5 : 6));
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
   static constexpr int kBBytes = (BN / CG) * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -85,7 +87,9 @@ struct GemmSmem {
   // warp-private copy of the bias slice of the current tile (generic epilogues): up to 128 floats per epilogue warp
   static constexpr int kBiasBytesPerWarp = 1024;   // (second half: the column sums of the LayerNorm-folded epilogues)
   static constexpr int kBiasOffset = kStageOffset + EW * kStageBytesPerWarp;
-  static constexpr int kTotal = kBiasOffset + EW * kBiasBytesPerWarp + 1024 /* alignment slack */;
+  static constexpr int kRedBytesPerWarp = RED ? 2 * 4096 : 0;
+  static constexpr int kRedOffset = (kBiasOffset + EW * kBiasBytesPerWarp + 1023) / 1024 * 1024;
+  static constexpr int kTotal = kRedOffset + EW * kRedBytesPerWarp + 1024 /* alignment slack */;
   static_assert(kTotal <= 232448, "more than 227 KB of shared memory");
 };
 
@@ -147,8 +151,10 @@ ULLSAM_DEVICE void res_ln_second_pass(const GemmParams& p, int row0, int half, i
 // twice the warps to hide the TMEM / global latencies of the epilogue and to spread the GELU arithmetic).
 template <int BN, int EPI, int CG = 1, int EW = 8>
 __global__ void __launch_bounds__((GEMM_EPI_WARP0 + EW) * 32, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using L = GemmSmem<BN, CG, EW>;
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC /* EPI_RES_RED: the fp32 output, 32 x 32 boxes; otherwise unused */, const GemmParams p) {
+  using L = GemmSmem<BN, CG, EW, EPI == EPI_RES_RED>;
+  static_assert(EPI != EPI_RES_RED || (BN == 256 && EW == 8), "EPI_RES_RED: 256-wide tiles, 8 epilogue warps");
   static_assert(EW == 8 || (EPI != EPI_LN_BF16 && EPI != EPI_LN_NCHW && EPI != EPI_LN_RES && EPI != EPI_UP1 && EPI != EPI_MASK),
                 "the LayerNorm / decoder epilogues assume two warps per row");
   static_assert(CG == 1 || BN == 256, "the CTA-pair kernel is built for 256-wide N tiles");
@@ -855,7 +861,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
           }
-          if constexpr (EPI == EPI_BF16 || kIsGelu || kIsQkv) {
+          if constexpr (EPI == EPI_RES_RED) {
+            // out[32 rows][32 columns] += acc + bias, the add done at the memory side: the chunk goes to a 4 KB box in shared
+            // memory (row = lane, 128-byte rows, 16-byte pieces XOR-swizzled with the row like the tensor map says: no bank
+            // conflicts) and leaves as ONE TMA reduce-add store.  Two boxes per warp; a box is reused once the store issued two
+            // chunks ago has read it.  Nothing here waits for global memory.
+            uint8_t* rbuf = smem + L::kRedOffset + (warp - GEMM_EPI_WARP0) * L::kRedBytesPerWarp + (c & 1) * 4096;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(rbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && tile_row0 < p.M) {
+              tma_reduce_add_2d(&tmC, rbuf, n0, tile_row0);   // rows beyond M are clipped by the tensor map
+              tma_store_commit();
+            }
+          } else if constexpr (EPI == EPI_BF16 || kIsGelu || kIsQkv) {
             // 32 bf16 per row = 64 bytes; staged with an 80-byte row pitch (conflict-free both ways)
             uint4* srow = reinterpret_cast<uint4*>(stage + lane * 80);
 #pragma unroll
@@ -1023,6 +1046,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
 
+  if constexpr (EPI == EPI_RES_RED) {
+    if (warp >= GEMM_EPI_WARP0 && lane == 0) tma_store_wait_all();   // every reduce-add of this warp has been performed
+  }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync();  // the peer's shared memory / barriers stay alive until both are done
   else __syncthreads();

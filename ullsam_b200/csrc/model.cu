@@ -620,6 +620,7 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
   // the neck.  (D % 256 == 0 and D <= 1024: ViT-B and ViT-L.)
   // ULLSAM_KMAX_EPI=0: the global attention takes its key-norm bound from a pre-pass over K instead of the QKV epilogue
   static const bool kmax_epi = !getenv_off("ULLSAM_KMAX_EPI");
+  static const bool proj_red = !getenv_off("ULLSAM_PROJ_RED");
   const bool foldable = D % 256 == 0 && D <= 128 * kStatSlots;
   const bool fold1 = foldable && (h->ln_fold & 1), fold2 = foldable && (h->ln_fold & 2);
   if (fold1 || fold2)
@@ -678,7 +679,9 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
         p.ln_w = b.ln2_w; p.ln_b = b.ln2_b; p.ln_eps = c.enc_ln_eps; p.out2 = h->xn_t; p.ln_partition = 0;
       }
       if (fold2) { p.out2 = h->xn_t; p.row_stats = h->row_stats; }
-      CKS(launch_gemm(fold2 ? EPI_RES_STATS : (fuse_ln2 ? EPI_RES_LN : EPI_RES_F32), h->ao, b.proj_w, p, sms, st));
+      // (plain residual add: done by the memory system through TMA reduce-add stores, EPI_RES_RED; ULLSAM_PROJ_RED=0: in the SM)
+      const int proj_epi = fold2 ? EPI_RES_STATS : (fuse_ln2 ? EPI_RES_LN : ((proj_red && D % 256 == 0) ? EPI_RES_RED : EPI_RES_F32));
+      CKS(launch_gemm(proj_epi, h->ao, b.proj_w, p, sms, st));
       mark(h, PC_GEMM_PROJ, st);
     }
     if (!fold2 && !fuse_ln2) {
