@@ -679,8 +679,9 @@ int encoder_chunk(ullsam_handle* h, const void* images, int dtype, int Bc, float
         p.ln_w = b.ln2_w; p.ln_b = b.ln2_b; p.ln_eps = c.enc_ln_eps; p.out2 = h->xn_t; p.ln_partition = 0;
       }
       if (fold2) { p.out2 = h->xn_t; p.row_stats = h->row_stats; }
-      // (plain residual add: done by the memory system through TMA reduce-add stores, EPI_RES_RED; ULLSAM_PROJ_RED=0: in the SM)
-      const int proj_epi = fold2 ? EPI_RES_STATS : (fuse_ln2 ? EPI_RES_LN : ((proj_red && D % 256 == 0) ? EPI_RES_RED : EPI_RES_F32));
+      // (plain residual add: done by the memory system through TMA reduce-add stores, EPI_RES_RED; ULLSAM_PROJ_RED=0: in the SM.
+      //  ViT-B only: at D = 1024 the variant's four pipeline stages cost more than its epilogue saves — proj 350 vs 315 us)
+      const int proj_epi = fold2 ? EPI_RES_STATS : (fuse_ln2 ? EPI_RES_LN : ((proj_red && D % 256 == 0 && D <= 768) ? EPI_RES_RED : EPI_RES_F32));
       CKS(launch_gemm(proj_epi, h->ao, b.proj_w, p, sms, st));
       mark(h, PC_GEMM_PROJ, st);
     }
