@@ -1103,7 +1103,7 @@ size_t ullsam_workspace_bytes(const ullsam_handle* h, int B, int R) {
   if (!h) return 0;
   const size_t D = h->cfg.embed_dim, M = h->cfg.mlp_dim;
   const size_t Bc = static_cast<size_t>(B < kEncChunk ? B : kEncChunk);
-  size_t enc = Bc * (4096 * D * 4 + 4 * 4900 * D * 2 + 4096 * D * 2 + 4096 * M * 2 + 4096 * 256 * 4);
+  size_t enc = Bc * (4096 * D * 4 + 4 * 4900 * D * 2 + 4096 * D * 2 + 4096 * M * 2 + 4096 * 256 * 4 + 4096 * kStatSlots * 8);
   const size_t Nt = 16;
   size_t dec = static_cast<size_t>(R) * (4096 * (256 * 4 + 256 * 2 + 384 * 2 + 128 * 2) + 16384 * 64 * 2 + Nt * 8 * 4096 * 4);
   return enc + dec;
